@@ -1,0 +1,142 @@
+/* rm_radar_b200 — C ABI of the B200-native detect + locate hot path.
+ *
+ * The reference (zmsbruce/rm_radar) exposes this path as C++ classes in four shared libraries
+ * (src/radar.h:15-18); it has no FFI layer, so this C ABI is the boundary a binding would target.
+ * Each entry point names the reference interface it replaces.  include/radar.hpp rebuilds the
+ * reference's C++ class surface (radar::Detector / RobotDetector / Locator / Robot) on top of it.
+ *
+ * Conventions: every function returns 0 on success or a negative rmr_status; rmr_last_error()
+ * returns the message of the last failure on the calling thread.  Handles own all device memory,
+ * streams and pinned buffers (reference: detector.cpp:151-161) and are NOT thread-safe, exactly
+ * like the reference objects (detector.h: single buffer set).  Inputs are borrowed for the duration
+ * of the call.  Images are BGR u8 HWC (cv::Mat CV_8UC3), clouds are float xyz with a byte stride
+ * (pcl::PointXYZ = 16).  No CPU fallback exists: without a CUDA device creation fails.
+ */
+#ifndef RM_RADAR_B200_H
+#define RM_RADAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMR_MAX_ARMORS 16
+
+typedef enum rmr_status {
+    RMR_OK = 0,
+    RMR_ERR_INVALID_ARGUMENT = -1, /* std::invalid_argument in the reference ctors (detector.cpp:80,181) */
+    RMR_ERR_RUNTIME = -2,          /* std::runtime_error (common.h:31-39, detector.cpp:184,199,205) */
+    RMR_ERR_CUDA = -3              /* CUDA_CHECK / CUDA_CHECK_NOEXCEPT failures (common.h:31-62) */
+} rmr_status;
+
+/* radar::Detection — src/detect/detection.h:25-68 (six floats, standard layout) */
+typedef struct rmr_detection {
+    float x, y, width, height, label, confidence;
+} rmr_detection_t;
+
+/* radar::Robot — src/robot/robot.h:53-164, the fields the hot path fills */
+typedef struct rmr_robot {
+    float rect[4];             /* rect_  (x, y, w, h) in frame pixels */
+    int32_t has_rect;
+    int32_t is_detected;       /* armors_.has_value()  (robot.h:65) */
+    int32_t label;             /* enum Label, robot.h:32-45 */
+    float confidence;
+    int32_t n_armors;
+    rmr_detection_t armors[RMR_MAX_ARMORS]; /* frame coordinates (robot.cpp:68-73) */
+    int32_t is_located;        /* location_.has_value() (robot.h:73) */
+    float location[3];         /* metres, world (robot.h:93-95) */
+    int32_t cluster;           /* diagnostic: chosen cluster id (-1 = unclustered group) */
+    int32_t cluster_points;    /* diagnostic: points averaged */
+} rmr_robot_t;
+
+typedef struct rmr_detector rmr_detector_t;
+typedef struct rmr_robot_detector rmr_robot_detector_t;
+typedef struct rmr_locator rmr_locator_t;
+
+const char* rmr_last_error(void);
+int rmr_device_count(int* count);
+
+/* ---- radar::Detector — src/detect/detector.h:84-134 ---------------------------------------- */
+/* Detector::Detector(engine_path, classes, image_size, max_batch_size, opt_batch_size, nms_thresh,
+ *   conf_thresh, input_width, input_height, input_name, input_channels, opt_level) detector.h:87-93.
+ * engine_path: a `.rmeng` file built by `python -m rm_radar_b200.engine model.onnx model.rmeng`
+ * (stands where the TensorRT `.engine` cache stands, detector.cpp:74-99).
+ * compat != 0 reproduces the reference's int-truncated letterbox geometry. */
+int rmr_detector_create(rmr_detector_t** out, const char* engine_path, int classes, int image_width,
+                        int image_height, int max_batch_size, float nms_thresh, float conf_thresh,
+                        int input_width, int input_height, int compat, int device);
+void rmr_detector_destroy(rmr_detector_t* d);
+/* Detector::detect(const cv::Mat&) -> std::vector<Detection>  (detector.h:117-134, single image) */
+int rmr_detector_detect(rmr_detector_t* d, const uint8_t* bgr, int width, int height, int stride_bytes,
+                        rmr_detection_t* out, int capacity, int* count);
+/* Detector::detect(container of cv::Mat) -> vector<vector<Detection>>  (batch);
+ * out is [n_images][capacity], counts is [n_images] */
+int rmr_detector_detect_batch(rmr_detector_t* d, const uint8_t* const* bgr, const int* widths, const int* heights,
+                              const int* strides_bytes, int n_images, rmr_detection_t* out, int capacity,
+                              int* counts);
+/* inspection for parity tests: network input of the last call as float [n][3][H][W] (blobKernel
+ * layout, detector.cu:151-171) and the head output [n][4+classes][anchors] (TensorRT output layout) */
+int rmr_detector_last_input(rmr_detector_t* d, float* out, int n_images);
+int rmr_detector_last_output(rmr_detector_t* d, float* out, int n_images);
+int rmr_detector_info(rmr_detector_t* d, int* anchors, int* classes, int* kernel_launches, double* flops_per_image);
+int rmr_detector_set_stream(rmr_detector_t* d, void* cuda_stream);
+
+/* ---- radar::RobotDetector — src/detect/detector.h:171-190 ---------------------------------- */
+/* RobotDetector::RobotDetector(car_path, armor_path, image_size, armor_classes, max_cars, opt_cars,
+ *   iou_thresh, car_nms, car_conf, armor_nms, armor_conf, input_width, input_height, ...) */
+int rmr_robot_detector_create(rmr_robot_detector_t** out, const char* car_engine, const char* armor_engine,
+                              int image_width, int image_height, int armor_classes, int max_cars,
+                              float iou_thresh, float car_nms_thresh, float car_conf_thresh,
+                              float armor_nms_thresh, float armor_conf_thresh, int input_width, int input_height,
+                              int compat, int device);
+void rmr_robot_detector_destroy(rmr_robot_detector_t* d);
+/* RobotDetector::detect(const cv::Mat&) -> std::vector<Robot>   (detector.cpp:413-455) */
+int rmr_robot_detector_detect(rmr_robot_detector_t* d, const uint8_t* bgr, int width, int height, int stride_bytes,
+                              rmr_robot_t* out, int capacity, int* count);
+/* same, frame already resident in device memory (HBM): no host->device copy */
+int rmr_robot_detector_detect_device(rmr_robot_detector_t* d, const void* dev_bgr, int width, int height,
+                                     int stride_bytes, rmr_robot_t* out, int capacity, int* count);
+/* diagnostics of the last call: car detections (frame coords) and per-car armour detections (ROI coords) */
+int rmr_robot_detector_last_cars(rmr_robot_detector_t* d, rmr_detection_t* out, int capacity, int* count);
+int rmr_robot_detector_last_armors(rmr_robot_detector_t* d, int car_index, rmr_detection_t* out, int capacity,
+                                   int* count);
+int rmr_robot_detector_set_stream(rmr_robot_detector_t* d, void* cuda_stream);
+/* kernels launched and conv FLOPs executed by the last detect call (bench accounting) */
+int rmr_robot_detector_last_stats(rmr_robot_detector_t* d, int* kernel_launches, double* conv_flops, int* n_cars);
+rmr_detector_t* rmr_robot_detector_car(rmr_robot_detector_t* d);
+rmr_detector_t* rmr_robot_detector_armor(rmr_robot_detector_t* d);
+
+/* ---- radar::Locator — src/locate/locator.h:53-71 -------------------------------------------- */
+/* Locator::Locator(image_width, image_height, intrinsic, lidar_to_camera, world_to_camera, zoom_factor,
+ *   queue_size, min_depth_diff, max_depth_diff, cluster_tolerance, min_cluster_size, max_cluster_size,
+ *   max_distance)   locator.h:59-65.  Matrices are row-major (cv::Matx33f / Matx44f). */
+int rmr_locator_create(rmr_locator_t** out, int image_width, int image_height, const float intrinsic[9],
+                       const float lidar_to_camera[16], const float world_to_camera[16], float zoom_factor,
+                       int queue_size, float min_depth_diff, float max_depth_diff, float cluster_tolerance,
+                       int min_cluster_size, int max_cluster_size, float max_distance, int device);
+void rmr_locator_destroy(rmr_locator_t* l);
+/* Locator::update(const PointCloud<PointXYZ>::Ptr&)  locate.cpp:158-220; NULL / n == 0 = null / empty cloud */
+int rmr_locator_update(rmr_locator_t* l, const float* xyz, int n_points, int stride_bytes);
+int rmr_locator_update_device(rmr_locator_t* l, const void* dev_xyz, int n_points, int stride_bytes);
+/* Locator::cluster()  locate.cpp:231-264 */
+int rmr_locator_cluster(rmr_locator_t* l);
+/* Locator::search(std::vector<Robot>&)  locate.cpp:276-326: fills is_located / location */
+int rmr_locator_search(rmr_locator_t* l, rmr_robot_t* robots, int n_robots);
+int rmr_locator_set_stream(rmr_locator_t* l, void* cuda_stream);
+/* inspection for parity tests.  which: 0 depth, 1 background, 2 diff (float), 3 cluster-label image (int32) */
+int rmr_locator_image_size(rmr_locator_t* l, int* width, int* height);
+int rmr_locator_read_image(rmr_locator_t* l, int which, void* out);
+int rmr_locator_stats(rmr_locator_t* l, int* n_foreground, int* n_clusters);
+int rmr_locator_read_foreground(rmr_locator_t* l, float* xyz_pix, int capacity); /* [n][4]: x,y,z,pixel */
+
+/* ---- conv layer self-test (tests/bench only): tcgen05 path vs the CUDA-core checker --------- */
+/* runs one conv of the given shape on random data through both kernels on the current device and
+ * returns the max abs difference; also times the tcgen05 kernel (ms per launch over `iters`). */
+int rmr_conv_selftest(int n, int h_in, int w_in, int cin, int cout, int k, int stride, int act, int residual,
+                      int out_f32, unsigned seed, int iters, float* max_abs_diff, float* max_ref, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RM_RADAR_B200_H */

@@ -1,0 +1,358 @@
+"""rm_radar_b200 — B200-native detect + locate hot path of zmsbruce/rm_radar.
+
+Python host mirror of the reference's public classes (`/root/reference/src/radar.h:15-18`):
+`Detector`, `RobotDetector`, `Locator`, `Robot`, `Detection`, `Label` — same names, argument order,
+defaults and error behaviour as `detector.h:87-93,173-184`, `locator.h:59-71`, `robot.h:32-164` —
+over the C ABI in `include/rm_radar_b200.h`.  All computation happens in the CUDA library; there is
+no CPU fallback (importing works without a GPU, constructing an object does not).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import RadarError  # noqa: F401
+
+__all__ = ["Detector", "RobotDetector", "Locator", "Robot", "Detection", "Label", "RadarError",
+           "engine_path_for"]
+
+
+class Label(enum.IntEnum):
+    # enum Label — /root/reference/src/robot/robot.h:32-45 (same order as armor.onnx class names)
+    BlueHero = 0
+    BlueEngineer = 1
+    BlueInfantryThree = 2
+    BlueInfantryFour = 3
+    BlueInfantryFive = 4
+    RedHero = 5
+    RedEngineer = 6
+    RedInfantryThree = 7
+    RedInfantryFour = 8
+    RedInfantryFive = 9
+    BlueSentry = 10
+    RedSentry = 11
+
+
+@dataclass
+class Detection:
+    # radar::Detection — detection.h:25-68
+    x: float
+    y: float
+    width: float
+    height: float
+    label: float
+    confidence: float
+
+    def as_array(self):
+        return np.array([self.x, self.y, self.width, self.height, self.label, self.confidence], np.float32)
+
+
+@dataclass
+class Robot:
+    # radar::Robot — robot.h:53-164 (optional-valued fields are None when unset)
+    rect: tuple | None = None
+    label: int | None = None
+    confidence: float | None = None
+    armors: list | None = None
+    location: tuple | None = None
+    cluster: int | None = None
+    cluster_points: int = 0
+
+    def isDetected(self) -> bool:   # robot.h:65
+        return self.armors is not None
+
+    def isLocated(self) -> bool:    # robot.h:73
+        return self.location is not None
+
+
+def engine_path_for(path: str) -> str:
+    """Resolve the reference's `engine_path` argument.  The reference loads `<x>.engine` or builds it
+    from the sibling `<x>.onnx` (detector.cpp:74-99).  We accept `.rmeng`, `.engine` or `.onnx` and
+    build `<x>.rmeng` from `<x>.onnx` when it does not exist yet."""
+    base, ext = os.path.splitext(path)
+    eng = path if ext == ".rmeng" else base + ".rmeng"
+    if os.path.exists(eng):
+        return eng
+    onnx = base + ".onnx"
+    if not os.path.exists(onnx):
+        raise ValueError(f"neither {eng} nor {onnx} exists")   # std::invalid_argument, detector.cpp:80
+    from . import engine
+    try:
+        engine.build_engine(onnx, eng)
+    except OSError:
+        # read-only model directory: cache next to the package instead
+        cache = os.path.join(os.path.dirname(os.path.abspath(__file__)), "engines")
+        os.makedirs(cache, exist_ok=True)
+        eng = os.path.join(cache, os.path.basename(base) + ".rmeng")
+        if not os.path.exists(eng):
+            engine.build_engine(onnx, eng)
+    return eng
+
+
+def _as_bgr(image: np.ndarray) -> np.ndarray:
+    if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
+        raise ValueError("image must be HxWx3 uint8 (BGR)")
+    if not image.flags.c_contiguous and image.strides[1:] != (3, 1):
+        image = np.ascontiguousarray(image)
+    return image
+
+
+def _dets(buf, n):
+    return [Detection(*buf[i].astuple()) for i in range(n)]
+
+
+class Detector:
+    """radar::Detector — detector.h:84-134."""
+
+    def __init__(self, engine_path, classes, image_size, max_batch_size, opt_batch_size=None, nms_thresh=0.65,
+                 conf_thresh=0.25, input_width=640, input_height=640, input_name="images", input_channels=3,
+                 opt_level=3, *, compat=True, device=0):
+        if input_channels != 3:
+            raise ValueError("input_channels must be 3")
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        w, h = image_size
+        eng = engine_path_for(os.fspath(engine_path))
+        _lib.check(self._lib.rmr_detector_create(C.byref(self._h), eng.encode(), classes, w, h, max_batch_size,
+                                                 nms_thresh, conf_thresh, input_width, input_height, int(compat),
+                                                 device))
+        self.classes = classes
+        self.max_batch_size = max_batch_size
+        self.input_size = (input_width, input_height)
+        self._cap = 256
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.rmr_detector_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def detect(self, images):
+        """One HxWx3 BGR uint8 array → list[Detection]; a sequence of arrays → list[list[Detection]]."""
+        if isinstance(images, np.ndarray):
+            img = _as_bgr(images)
+            out = (_lib.Detection * self._cap)()
+            n = C.c_int()
+            _lib.check(self._lib.rmr_detector_detect(self._h, img.ctypes.data, img.shape[1], img.shape[0],
+                                                     img.strides[0], out, self._cap, C.byref(n)))
+            return _dets(out, min(n.value, self._cap))
+        imgs = [_as_bgr(i) for i in images]
+        k = len(imgs)
+        if k == 0:
+            return []
+        ptrs = (C.c_void_p * k)(*[i.ctypes.data for i in imgs])
+        ws = (C.c_int * k)(*[i.shape[1] for i in imgs])
+        hs = (C.c_int * k)(*[i.shape[0] for i in imgs])
+        ss = (C.c_int * k)(*[i.strides[0] for i in imgs])
+        out = (_lib.Detection * (self._cap * k))()
+        counts = (C.c_int * k)()
+        _lib.check(self._lib.rmr_detector_detect_batch(self._h, ptrs, ws, hs, ss, k, out, self._cap, counts))
+        return [[Detection(*out[i * self._cap + j].astuple()) for j in range(min(counts[i], self._cap))]
+                for i in range(k)]
+
+    # -- inspection (tests) --
+    def last_input(self, n=1):
+        w, h = self.input_size
+        out = np.empty((n, 3, h, w), np.float32)
+        _lib.check(self._lib.rmr_detector_last_input(self._h, out.ctypes.data, n))
+        return out
+
+    def last_output(self, n=1):
+        a = C.c_int()
+        _lib.check(self._lib.rmr_detector_info(self._h, C.byref(a), None, None, None))
+        out = np.empty((n, 4 + self.classes, a.value), np.float32)
+        _lib.check(self._lib.rmr_detector_last_output(self._h, out.ctypes.data, n))
+        return out
+
+    def set_stream(self, cuda_stream: int):
+        _lib.check(self._lib.rmr_detector_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+
+class _DetectorView(Detector):
+    def __init__(self, lib, handle, classes, input_size):   # borrowed handle: never destroyed
+        self._lib, self._h, self.classes, self.input_size, self._cap = lib, C.c_void_p(handle), classes, input_size, 256
+
+    def __del__(self):
+        pass
+
+
+def _robot_from_rec(r) -> Robot:
+    robot = Robot()
+    if r.has_rect:
+        robot.rect = tuple(r.rect)
+    if r.is_detected:
+        robot.label = int(r.label)
+        robot.confidence = float(r.confidence)
+        robot.armors = [Detection(*r.armors[i].astuple()) for i in range(r.n_armors)]
+    if r.is_located:
+        robot.location = tuple(r.location)
+        robot.cluster = int(r.cluster)
+        robot.cluster_points = int(r.cluster_points)
+    return robot
+
+
+class RobotDetector:
+    """radar::RobotDetector — detector.h:171-190."""
+
+    def __init__(self, car_path, armor_path, image_size, armor_classes, max_cars, opt_cars, iou_thresh=0.75,
+                 car_nms_thresh=0.65, car_conf_thresh=0.25, armor_nms_thresh=0.65, armor_conf_thresh=0.50,
+                 input_width=640, input_height=640, input_name="images", input_channels=3, opt_level=5, *,
+                 compat=True, device=0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        w, h = image_size
+        car = engine_path_for(os.fspath(car_path))
+        armor = engine_path_for(os.fspath(armor_path))
+        _lib.check(self._lib.rmr_robot_detector_create(
+            C.byref(self._h), car.encode(), armor.encode(), w, h, armor_classes, max_cars, iou_thresh,
+            car_nms_thresh, car_conf_thresh, armor_nms_thresh, armor_conf_thresh, input_width, input_height,
+            int(compat), device))
+        self.max_cars = max_cars
+        self.armor_classes = armor_classes
+        self.input_size = (input_width, input_height)
+        self._recs = (_lib.RobotRec * max_cars)()
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.rmr_robot_detector_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def detect(self, image: np.ndarray) -> list:
+        """RobotDetector::detect(const cv::Mat&) — detector.cpp:413-455."""
+        img = _as_bgr(image)
+        n = C.c_int()
+        _lib.check(self._lib.rmr_robot_detector_detect(self._h, img.ctypes.data, img.shape[1], img.shape[0],
+                                                       img.strides[0], self._recs, self.max_cars, C.byref(n)))
+        return [_robot_from_rec(self._recs[i]) for i in range(min(n.value, self.max_cars))]
+
+    def detect_records(self, ptr: int, width: int, height: int, stride: int, device_ptr: bool):
+        """Raw-record variant used by the bench: returns (ctypes RobotRec array, count)."""
+        n = C.c_int()
+        fn = self._lib.rmr_robot_detector_detect_device if device_ptr else self._lib.rmr_robot_detector_detect
+        _lib.check(fn(self._h, C.c_void_p(ptr), width, height, stride, self._recs, self.max_cars, C.byref(n)))
+        return self._recs, min(n.value, self.max_cars)
+
+    def last_cars(self):
+        out = (_lib.Detection * 64)()
+        n = C.c_int()
+        _lib.check(self._lib.rmr_robot_detector_last_cars(self._h, out, 64, C.byref(n)))
+        return _dets(out, min(n.value, 64))
+
+    def last_armors(self, car_index):
+        out = (_lib.Detection * 64)()
+        n = C.c_int()
+        _lib.check(self._lib.rmr_robot_detector_last_armors(self._h, car_index, out, 64, C.byref(n)))
+        return _dets(out, min(n.value, 64))
+
+    def last_stats(self):
+        k, f, c = C.c_int(), C.c_double(), C.c_int()
+        _lib.check(self._lib.rmr_robot_detector_last_stats(self._h, C.byref(k), C.byref(f), C.byref(c)))
+        return dict(kernel_launches=k.value, conv_flops=f.value, n_cars=c.value)
+
+    def car_detector(self):
+        return _DetectorView(self._lib, self._lib.rmr_robot_detector_car(self._h), 1, self.input_size)
+
+    def armor_detector(self):
+        return _DetectorView(self._lib, self._lib.rmr_robot_detector_armor(self._h), self.armor_classes,
+                             self.input_size)
+
+    def set_stream(self, cuda_stream: int):
+        _lib.check(self._lib.rmr_robot_detector_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+
+class Locator:
+    """radar::Locator — locator.h:53-71."""
+
+    def __init__(self, image_width, image_height, intrinsic, lidar_to_camera, world_to_camera, zoom_factor=0.5,
+                 queue_size=3, min_depth_diff=500, max_depth_diff=4000, cluster_tolerance=400, min_cluster_size=8,
+                 max_cluster_size=1000, max_distance=29300, *, device=0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        K = np.ascontiguousarray(np.asarray(intrinsic, np.float32).reshape(9))
+        L = np.ascontiguousarray(np.asarray(lidar_to_camera, np.float32).reshape(16))
+        W = np.ascontiguousarray(np.asarray(world_to_camera, np.float32).reshape(16))
+        fp = C.POINTER(C.c_float)
+        _lib.check(self._lib.rmr_locator_create(
+            C.byref(self._h), image_width, image_height, K.ctypes.data_as(fp), L.ctypes.data_as(fp),
+            W.ctypes.data_as(fp), zoom_factor, queue_size, min_depth_diff, max_depth_diff, cluster_tolerance,
+            min_cluster_size, max_cluster_size, max_distance, device))
+        w, h = C.c_int(), C.c_int()
+        _lib.check(self._lib.rmr_locator_image_size(self._h, C.byref(w), C.byref(h)))
+        self.image_size_zoomed = (w.value, h.value)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.rmr_locator_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def update(self, cloud):
+        """Locator::update — locate.cpp:158-220.  cloud: [n,3] or [n,4] float32 (PointXYZ) or None."""
+        if cloud is None or len(cloud) == 0:
+            _lib.check(self._lib.rmr_locator_update(self._h, None, 0, 16))
+            return
+        pts = np.asarray(cloud)
+        if pts.dtype != np.float32 or pts.ndim != 2 or pts.shape[1] not in (3, 4) or not pts.flags.c_contiguous:
+            pts = np.ascontiguousarray(pts[:, :3], np.float32)
+        _lib.check(self._lib.rmr_locator_update(self._h, pts.ctypes.data, pts.shape[0], pts.strides[0]))
+
+    def update_device(self, dev_ptr: int, n_points: int, stride_bytes: int):
+        _lib.check(self._lib.rmr_locator_update_device(self._h, C.c_void_p(dev_ptr), n_points, stride_bytes))
+
+    def cluster(self):
+        """Locator::cluster — locate.cpp:231-264."""
+        _lib.check(self._lib.rmr_locator_cluster(self._h))
+
+    def search(self, robots):
+        """Locator::search(std::vector<Robot>&) — locate.cpp:276-326: sets `location` in place."""
+        n = len(robots)
+        if n == 0:
+            return
+        recs = (_lib.RobotRec * n)()
+        for i, r in enumerate(robots):
+            if r.rect is not None:
+                recs[i].rect = (C.c_float * 4)(*r.rect)
+                recs[i].has_rect = 1
+        _lib.check(self._lib.rmr_locator_search(self._h, recs, n))
+        for i, r in enumerate(robots):
+            if recs[i].is_located:
+                r.location = tuple(recs[i].location)
+                r.cluster = int(recs[i].cluster)
+                r.cluster_points = int(recs[i].cluster_points)
+
+    def search_records(self, recs, n):
+        _lib.check(self._lib.rmr_locator_search(self._h, recs, n))
+
+    # -- inspection (tests) --
+    def image(self, which: str) -> np.ndarray:
+        idx = {"depth": 0, "background": 1, "diff": 2, "labels": 3}[which]
+        w, h = self.image_size_zoomed
+        out = np.empty((h, w), np.int32 if idx == 3 else np.float32)
+        _lib.check(self._lib.rmr_locator_read_image(self._h, idx, out.ctypes.data))
+        return out
+
+    def stats(self):
+        f, c = C.c_int(), C.c_int()
+        _lib.check(self._lib.rmr_locator_stats(self._h, C.byref(f), C.byref(c)))
+        return dict(foreground=f.value, clusters=c.value)
+
+    def foreground(self):
+        n = self.stats()["foreground"]
+        out = np.empty((max(n, 1), 4), np.float32)
+        _lib.check(self._lib.rmr_locator_read_foreground(self._h, out.ctypes.data, n))
+        return out[:n, :3].copy(), out[:n, 3].view(np.int32).copy()
+
+    def set_stream(self, cuda_stream: int):
+        _lib.check(self._lib.rmr_locator_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+
+def conv_selftest(n, h, w, cin, cout, k, stride, act=1, residual=0, out_f32=0, seed=0, iters=0):
+    """tcgen05 conv vs the CUDA-core checker on random data; returns (max_abs_diff, max_ref, ms)."""
+    lib = _lib.load()
+    d, r, ms = C.c_float(), C.c_float(), C.c_float()
+    _lib.check(lib.rmr_conv_selftest(n, h, w, cin, cout, k, stride, act, residual, out_f32, seed, iters,
+                                     C.byref(d), C.byref(r), C.byref(ms)))
+    return d.value, r.value, ms.value

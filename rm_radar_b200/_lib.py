@@ -1,0 +1,112 @@
+"""ctypes binding of include/rm_radar_b200.h.  Fails loudly when the CUDA library is missing —
+there is no CPU fallback anywhere in the product path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librm_radar_b200.so")
+MAX_ARMORS = 16
+
+
+class Detection(C.Structure):
+    # radar::Detection — /root/reference/src/detect/detection.h:25-68
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("width", C.c_float), ("height", C.c_float),
+                ("label", C.c_float), ("confidence", C.c_float)]
+
+    def astuple(self):
+        return (self.x, self.y, self.width, self.height, self.label, self.confidence)
+
+
+class RobotRec(C.Structure):
+    _fields_ = [("rect", C.c_float * 4), ("has_rect", C.c_int32), ("is_detected", C.c_int32),
+                ("label", C.c_int32), ("confidence", C.c_float), ("n_armors", C.c_int32),
+                ("armors", Detection * MAX_ARMORS), ("is_located", C.c_int32), ("location", C.c_float * 3),
+                ("cluster", C.c_int32), ("cluster_points", C.c_int32)]
+
+
+# every symbol include/rm_radar_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "rmr_last_error", "rmr_device_count",
+    "rmr_detector_create", "rmr_detector_destroy", "rmr_detector_detect", "rmr_detector_detect_batch",
+    "rmr_detector_last_input", "rmr_detector_last_output", "rmr_detector_info", "rmr_detector_set_stream",
+    "rmr_robot_detector_create", "rmr_robot_detector_destroy", "rmr_robot_detector_detect",
+    "rmr_robot_detector_detect_device", "rmr_robot_detector_last_cars", "rmr_robot_detector_last_armors",
+    "rmr_robot_detector_set_stream", "rmr_robot_detector_last_stats", "rmr_robot_detector_car",
+    "rmr_robot_detector_armor",
+    "rmr_locator_create", "rmr_locator_destroy", "rmr_locator_update", "rmr_locator_update_device",
+    "rmr_locator_cluster", "rmr_locator_search", "rmr_locator_set_stream", "rmr_locator_image_size",
+    "rmr_locator_read_image", "rmr_locator_stats", "rmr_locator_read_foreground",
+    "rmr_conv_selftest",
+]
+
+_lib = None
+
+
+class RadarError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RadarError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(rm_radar_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.rmr_last_error.restype = C.c_char_p
+    vp, ci, cf, cd = C.c_void_p, C.c_int, C.c_float, C.c_double
+    P = C.POINTER
+    lib.rmr_device_count.argtypes = [P(ci)]
+    lib.rmr_detector_create.argtypes = [P(vp), C.c_char_p, ci, ci, ci, ci, cf, cf, ci, ci, ci, ci]
+    lib.rmr_detector_destroy.argtypes = [vp]
+    lib.rmr_detector_destroy.restype = None
+    lib.rmr_detector_detect.argtypes = [vp, vp, ci, ci, ci, P(Detection), ci, P(ci)]
+    lib.rmr_detector_detect_batch.argtypes = [vp, P(vp), P(ci), P(ci), P(ci), ci, P(Detection), ci, P(ci)]
+    lib.rmr_detector_last_input.argtypes = [vp, vp, ci]
+    lib.rmr_detector_last_output.argtypes = [vp, vp, ci]
+    lib.rmr_detector_info.argtypes = [vp, P(ci), P(ci), P(ci), P(cd)]
+    lib.rmr_detector_set_stream.argtypes = [vp, vp]
+    lib.rmr_robot_detector_create.argtypes = [P(vp), C.c_char_p, C.c_char_p, ci, ci, ci, ci, cf, cf, cf, cf, cf,
+                                              ci, ci, ci, ci]
+    lib.rmr_robot_detector_destroy.argtypes = [vp]
+    lib.rmr_robot_detector_destroy.restype = None
+    lib.rmr_robot_detector_detect.argtypes = [vp, vp, ci, ci, ci, P(RobotRec), ci, P(ci)]
+    lib.rmr_robot_detector_detect_device.argtypes = [vp, vp, ci, ci, ci, P(RobotRec), ci, P(ci)]
+    lib.rmr_robot_detector_last_cars.argtypes = [vp, P(Detection), ci, P(ci)]
+    lib.rmr_robot_detector_last_armors.argtypes = [vp, ci, P(Detection), ci, P(ci)]
+    lib.rmr_robot_detector_set_stream.argtypes = [vp, vp]
+    lib.rmr_robot_detector_last_stats.argtypes = [vp, P(ci), P(cd), P(ci)]
+    lib.rmr_robot_detector_car.argtypes = [vp]
+    lib.rmr_robot_detector_car.restype = vp
+    lib.rmr_robot_detector_armor.argtypes = [vp]
+    lib.rmr_robot_detector_armor.restype = vp
+    lib.rmr_locator_create.argtypes = [P(vp), ci, ci, P(cf), P(cf), P(cf), cf, ci, cf, cf, cf, ci, ci, cf, ci]
+    lib.rmr_locator_destroy.argtypes = [vp]
+    lib.rmr_locator_destroy.restype = None
+    lib.rmr_locator_update.argtypes = [vp, vp, ci, ci]
+    lib.rmr_locator_update_device.argtypes = [vp, vp, ci, ci]
+    lib.rmr_locator_cluster.argtypes = [vp]
+    lib.rmr_locator_search.argtypes = [vp, P(RobotRec), ci]
+    lib.rmr_locator_set_stream.argtypes = [vp, vp]
+    lib.rmr_locator_image_size.argtypes = [vp, P(ci), P(ci)]
+    lib.rmr_locator_read_image.argtypes = [vp, ci, vp]
+    lib.rmr_locator_stats.argtypes = [vp, P(ci), P(ci)]
+    lib.rmr_locator_read_foreground.argtypes = [vp, vp, ci]
+    lib.rmr_conv_selftest.argtypes = [ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, C.c_uint, ci, P(cf), P(cf), P(cf)]
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    """Constructors throw in the reference (std::invalid_argument / std::runtime_error); hot-path
+    CUDA failures abort.  Here every failure raises."""
+    if status == 0:
+        return
+    msg = load().rmr_last_error().decode(errors="replace")
+    if status == -1:
+        raise ValueError(msg)
+    raise RadarError(f"rm_radar_b200 status {status}: {msg}")

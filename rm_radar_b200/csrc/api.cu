@@ -1,0 +1,396 @@
+// extern "C" boundary (include/rm_radar_b200.h).  Exceptions become status codes + a thread-local
+// message; nothing here computes on the CPU.
+#include <cstring>
+#include <random>
+
+#include "../../include/rm_radar_b200.h"
+#include "detector.h"
+#include "locate.h"
+
+using namespace rmr;
+
+struct rmr_detector {
+    std::unique_ptr<Detector> owned;
+    Detector* impl = nullptr;
+};
+struct rmr_robot_detector {
+    std::unique_ptr<RobotDetector> impl;
+    rmr_detector car_view, armor_view;
+    int last_cars = 0;
+};
+struct rmr_locator {
+    std::unique_ptr<Locator> impl;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    int device = 0;
+};
+
+namespace {
+thread_local std::string g_last_error;
+
+template <class F>
+int guarded(F&& f) {
+    try {
+        f();
+        return RMR_OK;
+    } catch (const std::invalid_argument& e) {
+        g_last_error = e.what();
+        return RMR_ERR_INVALID_ARGUMENT;
+    } catch (const CudaError& e) {
+        g_last_error = e.what();
+        return RMR_ERR_CUDA;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return RMR_ERR_RUNTIME;
+    }
+}
+
+void fill_robot(const RobotRecord& r, rmr_robot_t* o) {
+    std::memset(o, 0, sizeof(*o));
+    std::memcpy(o->rect, r.rect, sizeof(o->rect));
+    o->has_rect = r.has_rect;
+    o->is_detected = r.detected;
+    o->label = r.detected ? r.label : -1;
+    o->confidence = r.confidence;
+    o->n_armors = std::min<int>(static_cast<int>(r.armors.size()), RMR_MAX_ARMORS);
+    for (int i = 0; i < o->n_armors; ++i) std::memcpy(&o->armors[i], &r.armors[i], sizeof(rmr_detection_t));
+    o->cluster = -2;
+}
+}  // namespace
+
+extern "C" {
+
+const char* rmr_last_error(void) { return g_last_error.c_str(); }
+
+int rmr_device_count(int* count) {
+    return guarded([&] { RMR_CUDA(cudaGetDeviceCount(count)); });
+}
+
+// ---------------------------------------------------------------- Detector
+int rmr_detector_create(rmr_detector_t** out, const char* engine_path, int classes, int image_width,
+                        int image_height, int max_batch_size, float nms_thresh, float conf_thresh, int input_width,
+                        int input_height, int compat, int device) {
+    return guarded([&] {
+        if (!out || !engine_path) throw std::invalid_argument("null argument");
+        auto h = std::make_unique<rmr_detector>();
+        h->owned = std::make_unique<Detector>(engine_path, classes, image_width, image_height, max_batch_size,
+                                              nms_thresh, conf_thresh, input_width, input_height, compat != 0, device);
+        h->impl = h->owned.get();
+        *out = h.release();
+    });
+}
+
+void rmr_detector_destroy(rmr_detector_t* d) { delete d; }
+
+int rmr_detector_detect(rmr_detector_t* d, const uint8_t* bgr, int width, int height, int stride_bytes,
+                        rmr_detection_t* out, int capacity, int* count) {
+    return guarded([&] {
+        if (!d || !out || !count) throw std::invalid_argument("null argument");
+        auto dets = d->impl->detect_host(bgr, width, height, stride_bytes);
+        *count = static_cast<int>(dets.size());
+        const int n = std::min<int>(*count, capacity);
+        std::memcpy(out, dets.data(), sizeof(rmr_detection_t) * n);
+    });
+}
+
+int rmr_detector_detect_batch(rmr_detector_t* d, const uint8_t* const* bgr, const int* widths, const int* heights,
+                              const int* strides_bytes, int n_images, rmr_detection_t* out, int capacity,
+                              int* counts) {
+    return guarded([&] {
+        if (!d || !out || !counts) throw std::invalid_argument("null argument");
+        auto res = d->impl->detect_host_batch(bgr, widths, heights, strides_bytes, n_images);
+        for (int i = 0; i < n_images; ++i) {
+            counts[i] = static_cast<int>(res[i].size());
+            const int n = std::min<int>(counts[i], capacity);
+            std::memcpy(out + static_cast<size_t>(i) * capacity, res[i].data(), sizeof(rmr_detection_t) * n);
+        }
+    });
+}
+
+int rmr_detector_last_input(rmr_detector_t* d, float* out, int n_images) {
+    return guarded([&] { d->impl->last_input(out, n_images); });
+}
+int rmr_detector_last_output(rmr_detector_t* d, float* out, int n_images) {
+    return guarded([&] { d->impl->last_output(out, n_images); });
+}
+int rmr_detector_info(rmr_detector_t* d, int* anchors, int* classes, int* kernel_launches, double* flops_per_image) {
+    return guarded([&] {
+        if (anchors) *anchors = d->impl->net().anchors();
+        if (classes) *classes = d->impl->classes();
+        if (kernel_launches) *kernel_launches = d->impl->last_launches();
+        if (flops_per_image) *flops_per_image = d->impl->net().flops_per_image();
+    });
+}
+int rmr_detector_set_stream(rmr_detector_t* d, void* cuda_stream) {
+    return guarded([&] { d->impl->set_stream(static_cast<cudaStream_t>(cuda_stream)); });
+}
+
+// ---------------------------------------------------------------- RobotDetector
+int rmr_robot_detector_create(rmr_robot_detector_t** out, const char* car_engine, const char* armor_engine,
+                              int image_width, int image_height, int armor_classes, int max_cars, float iou_thresh,
+                              float car_nms_thresh, float car_conf_thresh, float armor_nms_thresh,
+                              float armor_conf_thresh, int input_width, int input_height, int compat, int device) {
+    return guarded([&] {
+        if (!out || !car_engine || !armor_engine) throw std::invalid_argument("null argument");
+        auto h = std::make_unique<rmr_robot_detector>();
+        h->impl = std::make_unique<RobotDetector>(car_engine, armor_engine, image_width, image_height, armor_classes,
+                                                  max_cars, iou_thresh, car_nms_thresh, car_conf_thresh,
+                                                  armor_nms_thresh, armor_conf_thresh, input_width, input_height,
+                                                  compat != 0, device);
+        h->car_view.impl = &h->impl->car();
+        h->armor_view.impl = &h->impl->armor();
+        *out = h.release();
+    });
+}
+
+void rmr_robot_detector_destroy(rmr_robot_detector_t* d) { delete d; }
+
+static int robot_detect_common(rmr_robot_detector_t* d, const void* ptr, bool device_ptr, int width, int height,
+                               int stride_bytes, rmr_robot_t* out, int capacity, int* count) {
+    return guarded([&] {
+        if (!d || !out || !count) throw std::invalid_argument("null argument");
+        auto robots = device_ptr ? d->impl->detect_device(static_cast<const uint8_t*>(ptr), width, height, stride_bytes)
+                                 : d->impl->detect_host(static_cast<const uint8_t*>(ptr), width, height, stride_bytes);
+        *count = static_cast<int>(robots.size());
+        const int n = std::min<int>(*count, capacity);
+        for (int i = 0; i < n; ++i) fill_robot(robots[i], out + i);
+    });
+}
+
+int rmr_robot_detector_detect(rmr_robot_detector_t* d, const uint8_t* bgr, int width, int height, int stride_bytes,
+                              rmr_robot_t* out, int capacity, int* count) {
+    return robot_detect_common(d, bgr, false, width, height, stride_bytes, out, capacity, count);
+}
+int rmr_robot_detector_detect_device(rmr_robot_detector_t* d, const void* dev_bgr, int width, int height,
+                                     int stride_bytes, rmr_robot_t* out, int capacity, int* count) {
+    return robot_detect_common(d, dev_bgr, true, width, height, stride_bytes, out, capacity, count);
+}
+
+int rmr_robot_detector_last_cars(rmr_robot_detector_t* d, rmr_detection_t* out, int capacity, int* count) {
+    return guarded([&] {
+        const auto& c = d->impl->last_cars();
+        *count = static_cast<int>(c.size());
+        std::memcpy(out, c.data(), sizeof(rmr_detection_t) * std::min<int>(*count, capacity));
+    });
+}
+int rmr_robot_detector_last_armors(rmr_robot_detector_t* d, int car_index, rmr_detection_t* out, int capacity,
+                                   int* count) {
+    return guarded([&] {
+        const auto& a = d->impl->last_armors();
+        if (car_index < 0 || car_index >= static_cast<int>(a.size())) throw std::invalid_argument("car index");
+        *count = static_cast<int>(a[car_index].size());
+        std::memcpy(out, a[car_index].data(), sizeof(rmr_detection_t) * std::min<int>(*count, capacity));
+    });
+}
+int rmr_robot_detector_set_stream(rmr_robot_detector_t* d, void* cuda_stream) {
+    return guarded([&] { d->impl->set_stream(static_cast<cudaStream_t>(cuda_stream)); });
+}
+int rmr_robot_detector_last_stats(rmr_robot_detector_t* d, int* kernel_launches, double* conv_flops, int* n_cars) {
+    return guarded([&] {
+        if (kernel_launches) *kernel_launches = d->impl->last_launches();
+        if (conv_flops) *conv_flops = d->impl->last_flops();
+        if (n_cars) *n_cars = static_cast<int>(d->impl->last_cars().size());
+    });
+}
+rmr_detector_t* rmr_robot_detector_car(rmr_robot_detector_t* d) { return &d->car_view; }
+rmr_detector_t* rmr_robot_detector_armor(rmr_robot_detector_t* d) { return &d->armor_view; }
+
+// ---------------------------------------------------------------- Locator
+int rmr_locator_create(rmr_locator_t** out, int image_width, int image_height, const float intrinsic[9],
+                       const float lidar_to_camera[16], const float world_to_camera[16], float zoom_factor,
+                       int queue_size, float min_depth_diff, float max_depth_diff, float cluster_tolerance,
+                       int min_cluster_size, int max_cluster_size, float max_distance, int device) {
+    return guarded([&] {
+        if (!out || !intrinsic || !lidar_to_camera || !world_to_camera) throw std::invalid_argument("null argument");
+        RMR_CUDA(cudaSetDevice(device));
+        LocatorConfig cfg;
+        cfg.image_width = image_width; cfg.image_height = image_height;
+        std::memcpy(cfg.intrinsic, intrinsic, sizeof(cfg.intrinsic));
+        std::memcpy(cfg.lidar_to_camera, lidar_to_camera, sizeof(cfg.lidar_to_camera));
+        std::memcpy(cfg.world_to_camera, world_to_camera, sizeof(cfg.world_to_camera));
+        cfg.zoom_factor = zoom_factor; cfg.queue_size = queue_size;
+        cfg.min_depth_diff = min_depth_diff; cfg.max_depth_diff = max_depth_diff;
+        cfg.cluster_tolerance = cluster_tolerance;
+        cfg.min_cluster_size = min_cluster_size; cfg.max_cluster_size = max_cluster_size;
+        cfg.max_distance = max_distance;
+        auto h = std::make_unique<rmr_locator>();
+        h->device = device;
+        h->impl = std::make_unique<Locator>(cfg);
+        RMR_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
+        *out = h.release();
+    });
+}
+
+void rmr_locator_destroy(rmr_locator_t* l) {
+    if (!l) return;
+    cudaSetDevice(l->device);
+    if (l->own_stream) {
+        cudaStreamSynchronize(l->own_stream);
+        l->impl.reset();
+        cudaStreamDestroy(l->own_stream);
+    }
+    delete l;
+}
+
+int rmr_locator_update(rmr_locator_t* l, const float* xyz, int n_points, int stride_bytes) {
+    return guarded([&] {
+        RMR_CUDA(cudaSetDevice(l->device));
+        if (xyz && (stride_bytes % 4 != 0 || stride_bytes < 12)) throw std::invalid_argument("bad point stride");
+        l->impl->update_host(xyz, n_points, stride_bytes / 4, l->stream);
+    });
+}
+int rmr_locator_update_device(rmr_locator_t* l, const void* dev_xyz, int n_points, int stride_bytes) {
+    return guarded([&] {
+        RMR_CUDA(cudaSetDevice(l->device));
+        if (dev_xyz && (stride_bytes % 4 != 0 || stride_bytes < 12)) throw std::invalid_argument("bad point stride");
+        l->impl->update_device(static_cast<const float*>(dev_xyz), n_points, stride_bytes / 4, l->stream);
+    });
+}
+int rmr_locator_cluster(rmr_locator_t* l) {
+    return guarded([&] {
+        RMR_CUDA(cudaSetDevice(l->device));
+        l->impl->cluster(l->stream);
+    });
+}
+int rmr_locator_search(rmr_locator_t* l, rmr_robot_t* robots, int n_robots) {
+    return guarded([&] {
+        RMR_CUDA(cudaSetDevice(l->device));
+        if (n_robots <= 0) return;
+        std::vector<RectF> rects(n_robots);
+        std::vector<LocResult> res(n_robots);
+        for (int i = 0; i < n_robots; ++i)
+            rects[i] = RectF{robots[i].rect[0], robots[i].rect[1], robots[i].rect[2], robots[i].rect[3],
+                             robots[i].has_rect};
+        l->impl->search(rects.data(), res.data(), n_robots, l->stream);
+        for (int i = 0; i < n_robots; ++i) {
+            if (!res[i].located) continue;   // reference leaves location_ untouched (locate.cpp:300-302)
+            robots[i].is_located = 1;
+            robots[i].location[0] = res[i].x; robots[i].location[1] = res[i].y; robots[i].location[2] = res[i].z;
+            robots[i].cluster = res[i].cluster;
+            robots[i].cluster_points = res[i].npoints;
+        }
+    });
+}
+int rmr_locator_set_stream(rmr_locator_t* l, void* cuda_stream) {
+    return guarded([&] { l->stream = static_cast<cudaStream_t>(cuda_stream); });
+}
+int rmr_locator_image_size(rmr_locator_t* l, int* width, int* height) {
+    return guarded([&] { *width = l->impl->wz(); *height = l->impl->hz(); });
+}
+int rmr_locator_read_image(rmr_locator_t* l, int which, void* out) {
+    return guarded([&] {
+        RMR_CUDA(cudaSetDevice(l->device));
+        const void* src = nullptr;
+        switch (which) {
+            case 0: src = l->impl->depth_image(); break;
+            case 1: src = l->impl->background_image(); break;
+            case 2: src = l->impl->diff_image(); break;
+            case 3: src = l->impl->label_image(); break;
+            default: throw std::invalid_argument("which");
+        }
+        RMR_CUDA(cudaStreamSynchronize(l->stream));
+        RMR_CUDA(cudaMemcpy(out, src, sizeof(float) * l->impl->wz() * l->impl->hz(), cudaMemcpyDeviceToHost));
+    });
+}
+int rmr_locator_stats(rmr_locator_t* l, int* n_foreground, int* n_clusters) {
+    return guarded([&] {
+        RMR_CUDA(cudaSetDevice(l->device));
+        if (n_foreground) *n_foreground = l->impl->fg_count_sync(l->stream);
+        if (n_clusters) *n_clusters = l->impl->num_clusters_sync(l->stream);
+    });
+}
+int rmr_locator_read_foreground(rmr_locator_t* l, float* xyz_pix, int capacity) {
+    return guarded([&] {
+        RMR_CUDA(cudaSetDevice(l->device));
+        const int n = std::min(l->impl->fg_count_sync(l->stream), capacity);
+        RMR_CUDA(cudaMemcpy(xyz_pix, l->impl->fg_points(), sizeof(float) * 4 * n, cudaMemcpyDeviceToHost));
+    });
+}
+
+// ---------------------------------------------------------------- conv self-test
+int rmr_conv_selftest(int n, int h_in, int w_in, int cin, int cout, int k, int stride, int act, int residual,
+                      int out_f32, unsigned seed, int iters, float* max_abs_diff, float* max_ref, float* ms) {
+    return guarded([&] {
+        const int pad = k / 2;
+        const int h_out = (h_in + 2 * pad - k) / stride + 1, w_out = (w_in + 2 * pad - k) / stride + 1;
+        const int cout_pad = (cout + 15) / 16 * 16;
+        // views with channel offsets inside wider buffers, like Concat/Split produce
+        const int in_pitch = cin + 16, in_coff = 8, out_pitch = cout_pad + 16, out_coff = out_f32 ? 4 : 8;
+        const size_t in_elems = static_cast<size_t>(n) * h_in * w_in * in_pitch;
+        const size_t out_elems = static_cast<size_t>(n) * h_out * w_out * out_pitch;
+        const size_t w_elems = static_cast<size_t>(cout_pad) * k * k * cin;
+        std::mt19937 rng(seed);
+        std::uniform_real_distribution<float> dist(-1.f, 1.f);
+        std::vector<__half> h_in_buf(in_elems), h_w(w_elems), h_res(out_elems);
+        std::vector<float> h_bias(cout_pad);
+        for (auto& v : h_in_buf) v = __float2half(dist(rng));
+        const float wscale = 1.f / std::sqrt(static_cast<float>(k * k * cin));
+        for (size_t i = 0; i < w_elems; ++i) h_w[i] = __float2half(i / (static_cast<size_t>(k) * k * cin) < static_cast<size_t>(cout) ? dist(rng) * wscale * 2.f : 0.f);
+        for (auto& v : h_res) v = __float2half(dist(rng));
+        for (auto& v : h_bias) v = dist(rng) * 0.1f;
+        __half *d_in, *d_w, *d_res;
+        float* d_bias;
+        void *d_out_a, *d_out_b;
+        const size_t out_bytes = out_elems * (out_f32 ? 4 : 2);
+        RMR_CUDA(cudaMalloc(&d_in, in_elems * 2));
+        RMR_CUDA(cudaMalloc(&d_w, w_elems * 2));
+        RMR_CUDA(cudaMalloc(&d_res, out_elems * 2));
+        RMR_CUDA(cudaMalloc(&d_bias, cout_pad * 4));
+        RMR_CUDA(cudaMalloc(&d_out_a, out_bytes));
+        RMR_CUDA(cudaMalloc(&d_out_b, out_bytes));
+        RMR_CUDA(cudaMemcpy(d_in, h_in_buf.data(), in_elems * 2, cudaMemcpyHostToDevice));
+        RMR_CUDA(cudaMemcpy(d_w, h_w.data(), w_elems * 2, cudaMemcpyHostToDevice));
+        RMR_CUDA(cudaMemcpy(d_res, h_res.data(), out_elems * 2, cudaMemcpyHostToDevice));
+        RMR_CUDA(cudaMemcpy(d_bias, h_bias.data(), cout_pad * 4, cudaMemcpyHostToDevice));
+        RMR_CUDA(cudaMemset(d_out_a, 0, out_bytes));
+        RMR_CUDA(cudaMemset(d_out_b, 0, out_bytes));
+        ConvDesc d;
+        d.in = d_in; d.in_pitch = in_pitch; d.in_coff = in_coff; d.cin = cin; d.h_in = h_in; d.w_in = w_in;
+        d.out_pitch = out_pitch; d.out_coff = out_coff; d.cout = cout; d.out_f32 = out_f32;
+        d.h_out = h_out; d.w_out = w_out; d.k = k; d.stride = stride; d.act = act;
+        if (residual) { d.res = d_res; d.res_pitch = out_pitch; d.res_coff = 8; }
+        d.w = d_w; d.bias = d_bias; d.cout_pad = cout_pad; d.cin_pad = cin; d.n = n;
+        cudaStream_t s;
+        RMR_CUDA(cudaStreamCreate(&s));
+        d.out = d_out_a;
+        ConvLaunch l = make_conv_launch(d);
+        launch_conv_umma(l, s);
+        ConvDesc dr = d;
+        dr.out = d_out_b;
+        launch_conv_simt(dr, s);
+        RMR_CUDA(cudaStreamSynchronize(s));
+        std::vector<uint8_t> ha(out_bytes), hb(out_bytes);
+        RMR_CUDA(cudaMemcpy(ha.data(), d_out_a, out_bytes, cudaMemcpyDeviceToHost));
+        RMR_CUDA(cudaMemcpy(hb.data(), d_out_b, out_bytes, cudaMemcpyDeviceToHost));
+        float md = 0.f, mr = 0.f;
+        for (size_t i = 0; i < out_elems; ++i) {
+            const float a = out_f32 ? reinterpret_cast<float*>(ha.data())[i] : __half2float(reinterpret_cast<__half*>(ha.data())[i]);
+            const float b = out_f32 ? reinterpret_cast<float*>(hb.data())[i] : __half2float(reinterpret_cast<__half*>(hb.data())[i]);
+            const float df = std::fabs(a - b);
+            if (!(df <= md)) md = df;   // NaN propagates into md
+            mr = std::max(mr, std::fabs(b));
+        }
+        *max_abs_diff = md;
+        *max_ref = mr;
+        if (ms) {
+            *ms = 0.f;
+            if (iters > 0) {
+                cudaEvent_t e0, e1;
+                RMR_CUDA(cudaEventCreate(&e0));
+                RMR_CUDA(cudaEventCreate(&e1));
+                RMR_CUDA(cudaEventRecord(e0, s));
+                for (int i = 0; i < iters; ++i) launch_conv_umma(l, s);
+                RMR_CUDA(cudaEventRecord(e1, s));
+                RMR_CUDA(cudaEventSynchronize(e1));
+                float t;
+                RMR_CUDA(cudaEventElapsedTime(&t, e0, e1));
+                *ms = t / iters;
+                cudaEventDestroy(e0); cudaEventDestroy(e1);
+            }
+        }
+        cudaStreamDestroy(s);
+        cudaFree(d_in); cudaFree(d_w); cudaFree(d_res); cudaFree(d_bias); cudaFree(d_out_a); cudaFree(d_out_b);
+    });
+}
+
+}  // extern "C"

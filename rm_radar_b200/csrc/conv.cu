@@ -1,0 +1,532 @@
+// Implicit-GEMM convolution on 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands
+// staged by TMA) for the YOLOv8 Conv+bias+SiLU(+shortcut) blocks that the reference runs inside
+// TensorRT (/root/reference/src/detect/detector.h:122; FP16 engine built at detector.cpp:223-231).
+//
+// GEMM view:  D[M = N*Ho*Wo pixels, Cout] = A[M, K = taps*Cin] * W[Cout, K]^T
+//   * A is never materialised: for every filter tap one 5-D TMA box load fetches a
+//     [TN images][TH rows][TW cols][BK channels] patch of the NHWC activation at the tap's spatial
+//     offset.  Out-of-bounds box elements are zero-filled by TMA, which *is* the conv padding.
+//     Stride-2 layers view the activation as [N][H/2][2][W/2][2*Cpitch] (row/column parity split),
+//     so the same plain tiled TMA serves them: the column parity is a channel offset, the row
+//     parity is box coordinate 2.
+//   * the TMA box lands in shared memory as 128 pixel rows x BK fp16 (128 B or 64 B per row,
+//     hardware swizzled), which is exactly the K-major SWIZZLE_128B / SWIZZLE_64B UMMA operand.
+//   * W tiles [BLOCK_N][BK] come from a 2-D tensor map over the packed [Cout_pad][taps*Cin] weights.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue:
+//     tcgen05.ld -> +bias -> SiLU -> +residual -> fp16 (or fp32 for the head logits) -> NHWC store at
+//     the destination channel offset (Concat is just this offset).
+#include "conv.h"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+namespace rmr {
+
+namespace {
+
+constexpr int kStages = 5;
+constexpr int kStageBytes = 32768;   // 16 KB A (128 x 64 fp16) + 16 KB B (<=128 x 64 fp16)
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 128;
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const __grid_constant__ ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[kStages];
+    __shared__ __align__(8) uint64_t bar_empty[kStages];
+    __shared__ __align__(8) uint64_t bar_acc;
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // tile coordinates
+    int mt = blockIdx.x;
+    const int tile_w = mt % p.tiles_w;
+    mt /= p.tiles_w;
+    const int tile_h = mt % p.tiles_h;
+    const int tile_n = mt / p.tiles_h;
+    const int ow0 = tile_w * p.tw, oh0 = tile_h * p.th, n0 = tile_n * p.tn;
+    const int ch0 = blockIdx.y * p.block_n;   // first output channel of this CTA
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a);
+        tma_prefetch_desc(&tm_b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < kStages; ++i) {
+                mbar_init(smem_u32(&bar_full[i]), 1);
+                mbar_init(smem_u32(&bar_empty[i]), 1);
+            }
+            mbar_init(smem_u32(&bar_acc), 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    const int num_it = p.ntaps * p.kpt;
+    const uint32_t a_bytes = 128u * p.bk * 2u;
+    const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * p.bk * 2u;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < num_it; ++it) {
+                const int tap = it / p.kpt;
+                const int kc = it - tap * p.kpt;
+                const int4 t = p.tap[tap];
+                mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                const uint32_t full = smem_u32(&bar_full[stage]);
+                mbar_expect_tx(full, a_bytes + b_bytes);
+                const uint32_t sa = smem_base + stage * kStageBytes;
+                tma_load_5d(sa, &tm_a, full, p.cin_coff + t.x + kc * p.bk, ow0 + t.y, t.z, oh0 + t.w, n0);
+                tma_load_2d(sa + 16384, &tm_b, full, tap * p.cin + kc * p.bk, ch0);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int ksteps = p.bk / 16;
+            for (int it = 0; it < num_it; ++it) {
+                mbar_wait(smem_u32(&bar_full[stage]), phase);
+                tc_fence_after();
+                const uint32_t sa = smem_base + stage * kStageBytes;
+                const uint64_t adesc = umma_smem_desc(sa, p.sbo, p.layout);
+                const uint64_t bdesc = umma_smem_desc(sa + 16384, p.sbo, p.layout);
+                for (int k = 0; k < ksteps; ++k) {
+                    // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field
+                    umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, p.idesc, (it | k) != 0);
+                }
+                umma_commit(smem_u32(&bar_empty[stage]));   // frees the smem slot when the MMAs retire
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(smem_u32(&bar_acc));                // accumulator complete
+        }
+    } else {
+        // ---------------- epilogue: 4 warps, one TMEM lane quarter each ----------------
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int tw_i = row % p.tw;
+        const int th_i = (row / p.tw) % p.th;
+        const int tn_i = row / (p.tw * p.th);
+        const int ow = ow0 + tw_i, oh = oh0 + th_i, n = n0 + tn_i;
+        const bool valid = (ow < p.w_out) && (oh < p.h_out) && (n < p.n);
+        const size_t pix = (static_cast<size_t>(n) * p.h_out + oh) * p.w_out + ow;
+        const int nvalid = min(p.block_n, p.cout - ch0);   // real output channels in this tile
+
+        mbar_wait(smem_u32(&bar_acc), 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+            uint32_t v[16];
+            __syncwarp();
+            tmem_ld_16(taddr + c0, v);
+            tmem_ld_wait();
+            if (valid && c0 < nvalid) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float x = __uint_as_float(v[j]) + __ldg(p.bias + ch0 + c0 + j);
+                if (p.act) x = __fdividef(x, 1.0f + __expf(-x));
+                f[j] = x;
+            }
+            const int cnt = min(16, nvalid - c0);
+            if (p.res != nullptr) {
+                const __half* r = p.res + pix * p.res_pitch + p.res_coff + ch0 + c0;
+                if (cnt == 16) {
+                    const uint4 r0 = *reinterpret_cast<const uint4*>(r);
+                    const uint4 r1 = *reinterpret_cast<const uint4*>(r + 8);
+                    const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+                    const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 a = __half22float2(h0[j]);
+                        const float2 b = __half22float2(h1[j]);
+                        f[2 * j] += a.x; f[2 * j + 1] += a.y;
+                        f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
+                    }
+                } else {
+                    for (int j = 0; j < cnt; ++j) f[j] += __half2float(r[j]);
+                }
+            }
+            if (p.out_f32) {
+                float* o = static_cast<float*>(p.out) + pix * p.out_pitch + p.out_coff + ch0 + c0;
+                if (cnt == 16) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+                    for (int j = 0; j < cnt; ++j) o[j] = f[j];
+                }
+            } else {
+                __half* o = static_cast<__half*>(p.out) + pix * p.out_pitch + p.out_coff + ch0 + c0;
+                if (cnt == 16) {
+                    uint4 w0, w1;
+                    __half2* h0 = reinterpret_cast<__half2*>(&w0);
+                    __half2* h1 = reinterpret_cast<__half2*>(&w1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        h0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                        h1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+                    }
+                    reinterpret_cast<uint4*>(o)[0] = w0;
+                    reinterpret_cast<uint4*>(o)[1] = w1;
+                } else {
+                    for (int j = 0; j < cnt; ++j) o[j] = __float2half_rn(f[j]);
+                }
+            }
+            }
+        }
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Direct convolution on CUDA cores.  Used for the stem (Cin=3, padded to 4: K=36 is too thin for a
+// 128-wide MMA tile) and as the on-device checker the tests compare the tcgen05 path against.
+// One thread = one output pixel x 8 consecutive output channels.
+// ------------------------------------------------------------------------------------------
+__global__ void conv_simt_kernel(ConvDesc d) {
+    const int groups = (d.cout + 7) / 8;
+    const long total = static_cast<long>(d.n) * d.h_out * d.w_out * groups;
+    const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = static_cast<int>(idx % groups);
+    long pix = idx / groups;
+    const int ow = static_cast<int>(pix % d.w_out);
+    const int oh = static_cast<int>((pix / d.w_out) % d.h_out);
+    const int n = static_cast<int>(pix / (static_cast<long>(d.w_out) * d.h_out));
+    const int pad = d.k / 2;
+    const int ktot = d.k * d.k * d.cin_pad;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int r = 0; r < d.k; ++r) {
+        const int ih = oh * d.stride - pad + r;
+        if (ih < 0 || ih >= d.h_in) continue;
+        for (int s = 0; s < d.k; ++s) {
+            const int iw = ow * d.stride - pad + s;
+            if (iw < 0 || iw >= d.w_in) continue;
+            const __half* ip = d.in + ((static_cast<size_t>(n) * d.h_in + ih) * d.w_in + iw) * d.in_pitch + d.in_coff;
+            const __half* wp = d.w + static_cast<size_t>(g * 8) * ktot + (r * d.k + s) * d.cin_pad;
+            for (int c = 0; c < d.cin; ++c) {
+                const float x = __half2float(ip[c]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(x, __half2float(wp[static_cast<size_t>(j) * ktot + c]), acc[j]);
+            }
+        }
+    }
+    pix = (static_cast<long>(n) * d.h_out + oh) * d.w_out + ow;
+    for (int j = 0; j < 8; ++j) {
+        const int co = g * 8 + j;
+        if (co >= d.cout) break;
+        float x = acc[j] + d.bias[co];
+        if (d.act) x = x / (1.0f + __expf(-x));
+        if (d.res) x += __half2float(d.res[pix * d.res_pitch + d.res_coff + co]);
+        if (d.out_f32) static_cast<float*>(d.out)[pix * d.out_pitch + d.out_coff + co] = x;
+        else static_cast<__half*>(d.out)[pix * d.out_pitch + d.out_coff + co] = __float2half_rn(x);
+    }
+}
+
+// Stem: 3x3 stride-2, Cin = 3 (stored as 4), all Cout (<= 32) per thread, weights in shared memory.
+template <int COUT>
+__global__ void __launch_bounds__(128) conv_stem_kernel(ConvDesc d) {
+    __shared__ float ws[COUT * 36];
+    __shared__ float bs[COUT];
+    for (int i = threadIdx.x; i < COUT * 36; i += blockDim.x) ws[i] = __half2float(d.w[i]);
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = d.bias[i];
+    __syncthreads();
+    const long total = static_cast<long>(d.n) * d.h_out * d.w_out;
+    const long pix = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pix >= total) return;
+    const int ow = static_cast<int>(pix % d.w_out);
+    const int oh = static_cast<int>((pix / d.w_out) % d.h_out);
+    const int n = static_cast<int>(pix / (static_cast<long>(d.w_out) * d.h_out));
+    float x[36];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int ih = oh * 2 - 1 + r, iw = ow * 2 - 1 + s;
+            uint2 raw = make_uint2(0u, 0u);
+            if (ih >= 0 && ih < d.h_in && iw >= 0 && iw < d.w_in)
+                raw = *reinterpret_cast<const uint2*>(d.in + ((static_cast<size_t>(n) * d.h_in + ih) * d.w_in + iw) * 4);
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            x[(r * 3 + s) * 4 + 0] = a.x; x[(r * 3 + s) * 4 + 1] = a.y;
+            x[(r * 3 + s) * 4 + 2] = b.x; x[(r * 3 + s) * 4 + 3] = b.y;
+        }
+    }
+    __half* o = static_cast<__half*>(d.out) + pix * d.out_pitch + d.out_coff;
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 8) {
+        uint4 pack;
+        __half2* hp = reinterpret_cast<__half2*>(&pack);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            float y[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                float acc = bs[c0 + j + u];
+                const float* w = ws + (c0 + j + u) * 36;
+#pragma unroll
+                for (int i = 0; i < 36; ++i) acc = fmaf(x[i], w[i], acc);
+                y[u] = __fdividef(acc, 1.0f + __expf(-acc));
+            }
+            hp[j / 2] = __floats2half2_rn(y[0], y[1]);
+        }
+        *reinterpret_cast<uint4*>(o + c0) = pack;
+    }
+}
+
+// ---- memory-bound helpers: 8 channels (16 B) per thread, NHWC ----
+__global__ void maxpool5_kernel(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch,
+                                int out_coff, int n, int h, int w, int c8) {
+    const long total = static_cast<long>(n) * h * w * c8;
+    const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = static_cast<int>(idx % c8);
+    long pix = idx / c8;
+    const int x = static_cast<int>(pix % w);
+    const int y = static_cast<int>((pix / w) % h);
+    const int b = static_cast<int>(pix / (static_cast<long>(w) * h));
+    __half2 m[4];
+    const __half2 ninf = __floats2half2_rn(-65504.f, -65504.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = ninf;
+    for (int dy = -2; dy <= 2; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= h) continue;
+        for (int dx = -2; dx <= 2; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= w) continue;
+            const uint4 v = *reinterpret_cast<const uint4*>(
+                in + ((static_cast<size_t>(b) * h + yy) * w + xx) * in_pitch + in_coff + g * 8);
+            const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], hv[j]);
+        }
+    }
+    uint4 o;
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ho[j] = m[j];
+    *reinterpret_cast<uint4*>(out + pix * out_pitch + out_coff + g * 8) = o;
+}
+
+__global__ void upsample2_kernel(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch,
+                                 int out_coff, int n, int h_in, int w_in, int c8) {
+    const int h = h_in * 2, w = w_in * 2;
+    const long total = static_cast<long>(n) * h * w * c8;
+    const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = static_cast<int>(idx % c8);
+    const long pix = idx / c8;
+    const int x = static_cast<int>(pix % w);
+    const int y = static_cast<int>((pix / w) % h);
+    const int b = static_cast<int>(pix / (static_cast<long>(w) * h));
+    const uint4 v = *reinterpret_cast<const uint4*>(
+        in + ((static_cast<size_t>(b) * h_in + (y >> 1)) * w_in + (x >> 1)) * in_pitch + in_coff + g * 8);
+    *reinterpret_cast<uint4*>(out + pix * out_pitch + out_coff + g * 8) = v;
+}
+
+__global__ void copy_channels_kernel(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch,
+                                     int out_coff, long npix, int c8) {
+    const long total = npix * c8;
+    const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = static_cast<int>(idx % c8);
+    const long pix = idx / c8;
+    *reinterpret_cast<uint4*>(out + pix * out_pitch + out_coff + g * 8) =
+        *reinterpret_cast<const uint4*>(in + pix * in_pitch + in_coff + g * 8);
+}
+
+// ---- tensor map encoding through the driver entry point (no link-time libcuda dependency) ----
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        RMR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || p == nullptr)
+            throw CudaError("cuTensorMapEncodeTiled driver entry point not available");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+void encode(CUtensorMap* tm, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+            const cuuint32_t* box, CUtensorMapSwizzle swz) {
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = get_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, dims, strides_bytes, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+}
+
+int pick_block_n(int cout_pad) {
+    if (cout_pad <= 128) return cout_pad;
+    for (int bn = 128; bn >= 16; bn -= 16)
+        if (cout_pad % bn == 0) return bn;
+    return 16;
+}
+
+}  // namespace
+
+bool conv_umma_supported(const ConvDesc& d) {
+    if (d.cin % 32 != 0 || d.cin != d.cin_pad) return false;
+    if (!((d.k == 1 && d.stride == 1) || (d.k == 3 && (d.stride == 1 || d.stride == 2)))) return false;
+    if (d.stride == 2 && ((d.h_in | d.w_in) & 1)) return false;
+    if (d.in_pitch % 8 || d.in_coff % 8 || d.cout_pad % 16) return false;
+    return true;
+}
+
+ConvLaunch make_conv_launch(const ConvDesc& d) {
+    if (!conv_umma_supported(d)) throw CudaError("conv shape not supported by the tcgen05 path");
+    ConvLaunch l;
+    std::memset(&l, 0, sizeof(l));
+    ConvParams& p = l.p;
+    p.n = d.n; p.h_out = d.h_out; p.w_out = d.w_out; p.cout = d.cout;
+    p.block_n = pick_block_n(d.cout_pad);
+    p.bk = (d.cin % 64 == 0) ? 64 : 32;
+    p.kpt = d.cin / p.bk;
+    p.ntaps = d.k * d.k;
+    p.cin = d.cin; p.cin_coff = d.in_coff;
+    // tile shape: minimise the number of 128-pixel tiles (zero-filled lanes are wasted MMA rows)
+    long best = -1;
+    for (int tw = 128; tw >= 1; tw >>= 1) {
+        for (int th = 128 / tw; th >= 1; th >>= 1) {
+            const int tn = 128 / (tw * th);
+            const long tiles = static_cast<long>((d.w_out + tw - 1) / tw) * ((d.h_out + th - 1) / th) *
+                               ((d.n + tn - 1) / tn);
+            if (best < 0 || tiles < best) {
+                best = tiles; p.tw = tw; p.th = th; p.tn = tn;
+            }
+        }
+    }
+    p.tiles_w = (d.w_out + p.tw - 1) / p.tw;
+    p.tiles_h = (d.h_out + p.th - 1) / p.th;
+    p.tiles_n = (d.n + p.tn - 1) / p.tn;
+    const int S = d.stride;
+    for (int r = 0; r < d.k; ++r)
+        for (int s = 0; s < d.k; ++s) {
+            int4 t;
+            if (d.k == 1) t = make_int4(0, 0, 0, 0);
+            else if (S == 1) t = make_int4(0, s - 1, 0, r - 1);
+            else t = make_int4((s == 1 ? 0 : 1) * d.in_pitch, s == 0 ? -1 : 0, r == 1 ? 0 : 1, r == 0 ? -1 : 0);
+            p.tap[r * d.k + s] = t;
+        }
+    p.out = d.out; p.out_pitch = d.out_pitch; p.out_coff = d.out_coff; p.out_f32 = d.out_f32;
+    p.bias = d.bias; p.act = d.act;
+    p.res = d.res; p.res_pitch = d.res_pitch; p.res_coff = d.res_coff;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A/B=f16 (0), K-major both,
+    // N>>3 at [17,23), M>>4 at [24,29)
+    p.idesc = (1u << 4) | (static_cast<uint32_t>(p.block_n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+    p.sbo = (p.bk == 64) ? 1024u : 512u;
+    p.layout = (p.bk == 64) ? 2u : 4u;
+    const CUtensorMapSwizzle swz = (p.bk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+
+    // activation map: (S*Cpitch, W/S, S, H/S, N)
+    {
+        const cuuint64_t cp = static_cast<cuuint64_t>(d.in_pitch);
+        cuuint64_t dims[5] = {S * cp, static_cast<cuuint64_t>(d.w_in / S), static_cast<cuuint64_t>(S),
+                              static_cast<cuuint64_t>(d.h_in / S), static_cast<cuuint64_t>(d.n)};
+        cuuint64_t strides[4] = {S * cp * 2, d.w_in * cp * 2, S * d.w_in * cp * 2,
+                                 static_cast<cuuint64_t>(d.h_in) * d.w_in * cp * 2};
+        cuuint32_t box[5] = {static_cast<cuuint32_t>(p.bk), static_cast<cuuint32_t>(p.tw), 1u,
+                             static_cast<cuuint32_t>(p.th), static_cast<cuuint32_t>(p.tn)};
+        encode(&l.tm_a, const_cast<__half*>(d.in), 5, dims, strides, box, swz);
+    }
+    {
+        const cuuint64_t ktot = static_cast<cuuint64_t>(p.ntaps) * d.cin_pad;
+        cuuint64_t dims[2] = {ktot, static_cast<cuuint64_t>(d.cout_pad)};
+        cuuint64_t strides[1] = {ktot * 2};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(p.bk), static_cast<cuuint32_t>(p.block_n)};
+        encode(&l.tm_b, const_cast<__half*>(d.w), 2, dims, strides, box, swz);
+    }
+    l.grid = dim3(p.tiles_w * p.tiles_h * p.tiles_n, d.cout_pad / p.block_n, 1);
+    l.smem_bytes = kStages * kStageBytes + 1024;
+    l.flops = 2.0 * d.n * d.h_out * d.w_out * static_cast<double>(d.cout) * d.k * d.k * d.cin;
+    return l;
+}
+
+void conv_init() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kStages * kStageBytes + 1024));
+        get_encode_fn();
+    });
+}
+
+void launch_conv_umma(const ConvLaunch& l, cudaStream_t s) {
+    conv_init();
+    conv_umma_kernel<<<l.grid, kThreads, l.smem_bytes, s>>>(l.tm_a, l.tm_b, l.p);
+    RMR_CUDA(cudaGetLastError());
+}
+
+void launch_conv_simt(const ConvDesc& d, cudaStream_t s) {
+    if (d.cin_pad == 4 && d.k == 3 && d.stride == 2 && d.act == 1 && d.res == nullptr && !d.out_f32 &&
+        d.in_pitch == 4 && d.in_coff == 0 && (d.cout == 32 || d.cout == 16)) {
+        const long total = static_cast<long>(d.n) * d.h_out * d.w_out;
+        const int blocks = static_cast<int>((total + 127) / 128);
+        if (d.cout == 32) conv_stem_kernel<32><<<blocks, 128, 0, s>>>(d);
+        else conv_stem_kernel<16><<<blocks, 128, 0, s>>>(d);
+    } else {
+        const long total = static_cast<long>(d.n) * d.h_out * d.w_out * ((d.cout + 7) / 8);
+        conv_simt_kernel<<<static_cast<int>((total + 127) / 128), 128, 0, s>>>(d);
+    }
+    RMR_CUDA(cudaGetLastError());
+}
+
+void launch_maxpool5(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch, int out_coff, int n,
+                     int h, int w, int c, cudaStream_t s) {
+    const long total = static_cast<long>(n) * h * w * (c / 8);
+    maxpool5_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(in, in_pitch, in_coff, out, out_pitch,
+                                                                          out_coff, n, h, w, c / 8);
+    RMR_CUDA(cudaGetLastError());
+}
+
+void launch_upsample2(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch, int out_coff, int n,
+                      int h_in, int w_in, int c, cudaStream_t s) {
+    const long total = static_cast<long>(n) * h_in * 2 * w_in * 2 * (c / 8);
+    upsample2_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(in, in_pitch, in_coff, out, out_pitch,
+                                                                           out_coff, n, h_in, w_in, c / 8);
+    RMR_CUDA(cudaGetLastError());
+}
+
+void launch_copy_channels(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch, int out_coff,
+                          int n, int h, int w, int c, cudaStream_t s) {
+    const long npix = static_cast<long>(n) * h * w;
+    const long total = npix * (c / 8);
+    copy_channels_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(in, in_pitch, in_coff, out,
+                                                                               out_pitch, out_coff, npix, c / 8);
+    RMR_CUDA(cudaGetLastError());
+}
+
+}  // namespace rmr

@@ -1,0 +1,59 @@
+// Convolution layer launchers (implicit GEMM on tcgen05 + SIMT stem / checker + pooling ops).
+#pragma once
+#include "common.cuh"
+
+namespace rmr {
+
+// One Conv(+bias+SiLU+residual) op at a fixed batch size; activations NHWC fp16 with channel pitch.
+struct ConvDesc {
+    const __half* in = nullptr;
+    int in_pitch = 0, in_coff = 0, cin = 0, h_in = 0, w_in = 0;
+    void* out = nullptr;
+    int out_pitch = 0, out_coff = 0, cout = 0, out_f32 = 0, h_out = 0, w_out = 0;
+    int k = 1, stride = 1, act = 0;
+    const __half* res = nullptr;
+    int res_pitch = 0, res_coff = 0;
+    const __half* w = nullptr;   // [cout_pad][k*k][cin_pad] fp16
+    const float* bias = nullptr; // [cout_pad]
+    int cout_pad = 0, cin_pad = 0;
+    int n = 1;                   // batch
+};
+
+struct ConvParams {
+    int n, h_out, w_out, cout;
+    int block_n, bk, kpt, ntaps;      // kpt = k-blocks per tap
+    int tw, th, tn, tiles_w, tiles_h, tiles_n;
+    int4 tap[9];                      // (channel add, dw, h-parity, dh)
+    int cin_coff, cin;
+    void* out;
+    int out_pitch, out_coff, out_f32;
+    const float* bias;
+    int act;
+    const __half* res;
+    int res_pitch, res_coff;
+    uint32_t idesc, sbo, layout;
+};
+
+struct ConvLaunch {
+    CUtensorMap tm_a, tm_b;
+    ConvParams p;
+    dim3 grid;
+    int smem_bytes = 0;
+    double flops = 0;
+};
+
+void conv_init();   // one-time function attributes; must run outside stream capture
+bool conv_umma_supported(const ConvDesc& d);
+ConvLaunch make_conv_launch(const ConvDesc& d);
+void launch_conv_umma(const ConvLaunch& l, cudaStream_t s);
+// generic direct convolution on CUDA cores: the stem (Cin=3) and the on-device checker for tests
+void launch_conv_simt(const ConvDesc& d, cudaStream_t s);
+
+void launch_maxpool5(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch, int out_coff,
+                     int n, int h, int w, int c, cudaStream_t s);
+void launch_upsample2(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch, int out_coff,
+                      int n, int h_in, int w_in, int c, cudaStream_t s);
+void launch_copy_channels(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch, int out_coff,
+                          int n, int h, int w, int c, cudaStream_t s);
+
+}  // namespace rmr

@@ -1,0 +1,97 @@
+// Detector (one network) and RobotDetector (car -> armor cascade) on top of Net + the fused
+// pre/post-process kernels.  Mirrors radar::Detector / radar::RobotDetector
+// (/root/reference/src/detect/detector.h:84-190, detector.cpp:377-455).
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "net.h"
+#include "postprocess.h"
+#include "preprocess.h"
+
+namespace rmr {
+
+struct Roi {
+    int x, y, w, h;
+};
+
+class Detector {
+public:
+    Detector(const std::string& engine_path, int classes, int image_w, int image_h, int max_batch, float nms_thresh,
+             float conf_thresh, int input_w, int input_h, bool compat, int device);
+    ~Detector();
+
+    // single host image (Detector::detect(const cv::Mat&))
+    std::vector<Detection> detect_host(const uint8_t* bgr, int w, int h, int stride);
+    // batch of host images (Detector::detect(container))
+    std::vector<std::vector<Detection>> detect_host_batch(const uint8_t* const* bgr, const int* w, const int* h,
+                                                          const int* stride, int n);
+    // ROIs of a frame that already lives in device memory (the cascade's second stage)
+    std::vector<std::vector<Detection>> detect_device_rois(const uint8_t* dev_frame, int stride, const Roi* rois,
+                                                           int n);
+    void last_input(float* out, int n);    // [n][3][H][W] float
+    void last_output(float* out, int n);   // [n][4+nc][A] float
+    void set_stream(cudaStream_t s) { stream_ = s; }
+    cudaStream_t stream() const { return stream_; }
+    Net& net() { return *net_; }
+    int classes() const { return classes_; }
+    int max_batch() const { return max_batch_; }
+    int device() const { return device_; }
+    uint8_t* frame_buffer(size_t bytes);   // device staging for host frames (grows on demand)
+    int last_launches() const { return last_launches_; }
+
+private:
+    std::vector<std::vector<Detection>> run(const uint8_t* dev_frame, int stride, const Roi* rois, int n);
+
+    int classes_, image_w_, image_h_, max_batch_, input_w_, input_h_, device_;
+    float nms_thresh_, conf_thresh_;
+    bool compat_, ever_unclean_ = false;
+    cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
+    std::unique_ptr<Net> net_;
+    PostBuffers post_;
+    uint8_t* dev_frame_ = nullptr;
+    size_t dev_frame_bytes_ = 0;
+    uint8_t* pinned_frame_ = nullptr;
+    size_t pinned_frame_bytes_ = 0;
+    uint8_t* staging_ = nullptr;            // the reference's dev_border_ptr_: [max_batch][H*W*3] u8
+    LetterboxGeom *dev_geoms_ = nullptr, *pinned_geoms_ = nullptr;
+    Detection* pinned_out_ = nullptr;
+    int* pinned_counts_ = nullptr;
+    int last_launches_ = 0;
+};
+
+struct RobotRecord {
+    float rect[4];
+    bool has_rect = false, detected = false;
+    int label = -1;
+    float confidence = 0.f;
+    std::vector<Detection> armors;
+};
+
+class RobotDetector {
+public:
+    RobotDetector(const std::string& car_engine, const std::string& armor_engine, int image_w, int image_h,
+                  int armor_classes, int max_cars, float iou_thresh, float car_nms, float car_conf, float armor_nms,
+                  float armor_conf, int input_w, int input_h, bool compat, int device);
+    std::vector<RobotRecord> detect_host(const uint8_t* bgr, int w, int h, int stride);
+    std::vector<RobotRecord> detect_device(const uint8_t* dev_bgr, int w, int h, int stride);
+    void set_stream(cudaStream_t s) { car_->set_stream(s); armor_->set_stream(s); }
+    Detector& car() { return *car_; }
+    Detector& armor() { return *armor_; }
+    const std::vector<Detection>& last_cars() const { return last_cars_; }
+    const std::vector<std::vector<Detection>>& last_armors() const { return last_armors_; }
+    int last_launches() const { return last_launches_; }
+    double last_flops() const { return last_flops_; }
+
+private:
+    std::unique_ptr<Detector> car_, armor_;
+    int max_cars_;
+    float iou_thresh_;
+    std::vector<Detection> last_cars_;
+    std::vector<std::vector<Detection>> last_armors_;
+    int last_launches_ = 0;
+    double last_flops_ = 0;
+};
+
+}  // namespace rmr

@@ -1,0 +1,36 @@
+#pragma once
+#include "common.cuh"
+#include "net.h"
+#include "preprocess.h"
+
+namespace rmr {
+
+// Same POD as radar::Detection (/root/reference/src/detect/detection.h:25-68): six floats.
+struct Detection {
+    float x, y, width, height, label, confidence;
+};
+static_assert(sizeof(Detection) == 24, "Detection must stay a 6-float POD");
+
+constexpr int kMaxCandidates = 4096;   // per image, after the confidence threshold
+
+struct PostBuffers {
+    // device
+    float* cand = nullptr;        // [batch][kMaxCandidates][8]: x,y,w,h,label,conf,anchor,pad
+    int* cand_count = nullptr;    // [batch]
+    Detection* out = nullptr;     // [batch][max_out]
+    int* out_count = nullptr;     // [batch] (survivors, may exceed max_out -> truncated on write)
+    int max_out = 0;
+    int max_batch = 0;
+};
+
+void post_alloc(PostBuffers& pb, int max_batch, int max_out);
+void post_free(PostBuffers& pb);
+
+// Fused replacement for transposeKernel + decodeKernel + NMSKernel + the CPU NaN filter and
+// restoreDetection (detector.cu:185-360, 522-582; detector.cpp:258-268): reads the head logits in
+// place, thresholds first, and only the survivors reach the all-pairs NMS.
+void launch_postprocess(const std::vector<HeadLevel>& levels, int num_classes, int batch,
+                        const LetterboxGeom* dev_geoms, float conf_thresh, float nms_thresh, PostBuffers& pb,
+                        cudaStream_t s);
+
+}  // namespace rmr

@@ -1,0 +1,147 @@
+// Fused letterbox preprocess: bilinear resize + constant-128 border + BGR->RGB + 1/255 + fp16 NHWC,
+// replacing resizeKernel / copyMakeBorderKernel / blobKernel
+// (/root/reference/src/detect/detector.cu:40-81, 102-133, 151-171) and their call sites
+// (detector.cu:380-421 single frame, 439-502 ROI batch).  ROIs are read straight out of the
+// device-resident frame: no CPU crop + clone (detector.cpp:417-424), no second upload.
+//
+// Arithmetic is pinned to the oracle (oracle/detect_oracle.py: resize/copy_make_border/blob):
+// top-left aligned sampling, one IEEE rounding per operation (no FMA contraction), blend order
+// ((tl+tr)+bl)+br, truncating cast to u8, then u8 * (1/255.f) rounded once to fp16.
+//
+// Bug-compatible geometry: the reference truncates the float resized
+// size at the kernel call sites, so the bordered image can be 639 wide/high.  It is then written
+// with stride 639*3 into a persistent 640*640*3 staging buffer and read back with stride 640*3.
+// `clean` geometry (bordered size == 640x640) takes the single fused kernel; anything else goes
+// through the same persistent u8 staging buffer as the reference (two launches).
+#include "preprocess.h"
+
+namespace rmr {
+
+namespace {
+
+__device__ __forceinline__ unsigned char sample_u8(const unsigned char* __restrict__ src, int stride, int sw, int sh,
+                                                   int dw, int dh, int dx, int dy, int c) {
+    const float sy = __fdiv_rn(__fmul_rn(static_cast<float>(dy), static_cast<float>(sh)), static_cast<float>(dh));
+    const float sx = __fdiv_rn(__fmul_rn(static_cast<float>(dx), static_cast<float>(sw)), static_cast<float>(dw));
+    const int y0 = static_cast<int>(sy);
+    const int x0 = static_cast<int>(sx);
+    const int y1 = min(y0 + 1, sh - 1);
+    const int x1 = min(x0 + 1, sw - 1);
+    const float ly = __fsub_rn(sy, static_cast<float>(y0));
+    const float lx = __fsub_rn(sx, static_cast<float>(x0));
+    const float hy = __fsub_rn(1.f, ly);
+    const float hx = __fsub_rn(1.f, lx);
+    const float tl = __fmul_rn(__fmul_rn(static_cast<float>(src[y0 * stride + x0 * 3 + c]), hy), hx);
+    const float tr = __fmul_rn(__fmul_rn(static_cast<float>(src[y0 * stride + x1 * 3 + c]), hy), lx);
+    const float bl = __fmul_rn(__fmul_rn(static_cast<float>(src[y1 * stride + x0 * 3 + c]), ly), hx);
+    const float br = __fmul_rn(__fmul_rn(static_cast<float>(src[y1 * stride + x1 * 3 + c]), ly), lx);
+    const float v = __fadd_rn(__fadd_rn(__fadd_rn(tl, tr), bl), br);
+    return static_cast<unsigned char>(v);
+}
+
+__device__ __forceinline__ uint2 pack_rgb(unsigned char b, unsigned char g, unsigned char r) {
+    const float s = 1.f / 255.f;
+    const __half2 rg = __floats2half2_rn(__fmul_rn(static_cast<float>(r), s), __fmul_rn(static_cast<float>(g), s));
+    const __half2 b0 = __floats2half2_rn(__fmul_rn(static_cast<float>(b), s), 0.f);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&rg);
+    o.y = *reinterpret_cast<const uint32_t*>(&b0);
+    return o;
+}
+
+// one thread per network-input pixel; blockIdx.y = image slot
+__global__ void __launch_bounds__(256) letterbox_fused_kernel(const unsigned char* __restrict__ frame, int stride,
+                                                              const LetterboxGeom* __restrict__ geoms,
+                                                              __half* __restrict__ out, int out_w, int out_h) {
+    const LetterboxGeom g = geoms[blockIdx.y];
+    if (!g.clean) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= out_w * out_h) return;
+    const int x = idx % out_w, y = idx / out_w;
+    const int rx = x - g.left, ry = y - g.top;
+    unsigned char b = 128, gch = 128, r = 128;
+    if (rx >= 0 && rx < g.pw && ry >= 0 && ry < g.ph) {
+        const unsigned char* src = frame + static_cast<size_t>(g.src_y) * stride + g.src_x * 3;
+        b = sample_u8(src, stride, g.src_w, g.src_h, g.pw, g.ph, rx, ry, 0);
+        gch = sample_u8(src, stride, g.src_w, g.src_h, g.pw, g.ph, rx, ry, 1);
+        r = sample_u8(src, stride, g.src_w, g.src_h, g.pw, g.ph, rx, ry, 2);
+    }
+    reinterpret_cast<uint2*>(out)[static_cast<size_t>(blockIdx.y) * out_w * out_h + idx] = pack_rgb(b, gch, r);
+}
+
+// bug-compatible path, stage 1: resize + border into the persistent u8 staging slot with the
+// *actual* bordered stride (bw*3); threads outside bw x bh write nothing (stale bytes survive)
+__global__ void __launch_bounds__(256) letterbox_stage_kernel(const unsigned char* __restrict__ frame, int stride,
+                                                              const LetterboxGeom* __restrict__ geoms,
+                                                              unsigned char* __restrict__ staging, int out_w,
+                                                              int out_h) {
+    const LetterboxGeom g = geoms[blockIdx.y];
+    if (g.clean) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= out_w * out_h) return;
+    const int x = idx % out_w, y = idx / out_w;
+    if (x >= g.bw || y >= g.bh) return;
+    const int rx = x - g.left, ry = y - g.top;
+    unsigned char v[3] = {128, 128, 128};
+    if (rx >= 0 && rx < g.pw && ry >= 0 && ry < g.ph) {
+        const unsigned char* src = frame + static_cast<size_t>(g.src_y) * stride + g.src_x * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = sample_u8(src, stride, g.src_w, g.src_h, g.pw, g.ph, rx, ry, c);
+    }
+    unsigned char* dst = staging + static_cast<size_t>(blockIdx.y) * out_w * out_h * 3 + (y * g.stride_w + x) * 3;
+    dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2];
+}
+
+// stage 2: read the staging slot with the nominal stride (out_w*3), as blobKernel does
+__global__ void __launch_bounds__(256) letterbox_blob_kernel(const LetterboxGeom* __restrict__ geoms,
+                                                             const unsigned char* __restrict__ staging,
+                                                             __half* __restrict__ out, int out_w, int out_h) {
+    if (geoms[blockIdx.y].clean) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= out_w * out_h) return;
+    const unsigned char* s = staging + (static_cast<size_t>(blockIdx.y) * out_w * out_h + idx) * 3;
+    reinterpret_cast<uint2*>(out)[static_cast<size_t>(blockIdx.y) * out_w * out_h + idx] = pack_rgb(s[0], s[1], s[2]);
+}
+
+}  // namespace
+
+// PreParam(cv::Size, cv::Size) — /root/reference/src/detect/preparam.h:46-52, plus the call-site
+// integer geometry of detector.cu:393-410.
+LetterboxGeom make_letterbox_geom(int src_x, int src_y, int src_w, int src_h, int out_w, int out_h, bool compat) {
+    LetterboxGeom g{};
+    g.src_x = src_x; g.src_y = src_y; g.src_w = src_w; g.src_h = src_h;
+    const float height = static_cast<float>(src_h), width = static_cast<float>(src_w);
+    const float ratio = 1.f / std::min(static_cast<float>(out_h) / height, static_cast<float>(out_w) / width);
+    g.width = width; g.height = height; g.ratio = ratio;
+    g.dw = (static_cast<float>(out_w) - std::round(width / ratio)) * 0.5f;
+    g.dh = (static_cast<float>(out_h) - std::round(height / ratio)) * 0.5f;
+    const float pwf = width / ratio, phf = height / ratio;
+    g.pw = compat ? static_cast<int>(pwf) : static_cast<int>(std::round(pwf));
+    g.ph = compat ? static_cast<int>(phf) : static_cast<int>(std::round(phf));
+    g.pw = std::max(g.pw, 1);
+    g.ph = std::max(g.ph, 1);
+    g.top = static_cast<int>(std::round(g.dh - 0.1));
+    const int bottom = static_cast<int>(std::round(g.dh + 0.1));
+    g.left = static_cast<int>(std::round(g.dw - 0.1));
+    const int right = static_cast<int>(std::round(g.dw + 0.1));
+    g.bw = std::min(g.pw + g.left + right, out_w);
+    g.bh = std::min(g.ph + g.top + bottom, out_h);
+    g.clean = (g.pw + g.left + right == out_w && g.ph + g.top + bottom == out_h) ? 1 : 0;
+    g.stride_w = g.pw + g.left + right;
+    return g;
+}
+
+void launch_letterbox(const unsigned char* frame, int stride, const LetterboxGeom* dev_geoms, bool any_unclean,
+                      bool any_clean, int count, unsigned char* staging, __half* out, int out_w, int out_h,
+                      cudaStream_t s) {
+    if (count <= 0) return;
+    const dim3 grid((out_w * out_h + 255) / 256, count);
+    if (any_clean) letterbox_fused_kernel<<<grid, 256, 0, s>>>(frame, stride, dev_geoms, out, out_w, out_h);
+    if (any_unclean) {
+        letterbox_stage_kernel<<<grid, 256, 0, s>>>(frame, stride, dev_geoms, staging, out_w, out_h);
+        letterbox_blob_kernel<<<grid, 256, 0, s>>>(dev_geoms, staging, out, out_w, out_h);
+    }
+    RMR_CUDA(cudaGetLastError());
+}
+
+}  // namespace rmr

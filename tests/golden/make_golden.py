@@ -1,0 +1,71 @@
+"""Generates the committed fixtures under tests/golden/ from the reference's assets and the oracle.
+Run in the build container (needs /root/reference):   python tests/golden/make_golden.py
+  frames/0.jpg, frames/5.jpg   verbatim copies of assets/images (input data, not source)
+  clouds.npz                    assets/clouds 0..3 + every 4th point of background.pcd
+  expected.npz                  oracle outputs (fp32 ONNX via oracle/onnx_torch.py, compat letterbox)
+"""
+import os
+import shutil
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+from oracle import detect_oracle as do  # noqa: E402
+from oracle import locate_oracle as lo  # noqa: E402
+from oracle.onnx_torch import OnnxNet  # noqa: E402
+from tests import fixtures as fx  # noqa: E402
+
+
+def main():
+    import cv2
+    os.makedirs(os.path.join(HERE, "frames"), exist_ok=True)
+    for i in (0, 5):
+        shutil.copyfile(f"{REF}/assets/images/{i}.jpg", os.path.join(HERE, "frames", f"{i}.jpg"))
+    clouds = {f"c{i}": lo.read_pcd(f"{REF}/assets/clouds/{i}.pcd") for i in range(4)}
+    clouds["c5"] = lo.read_pcd(f"{REF}/assets/clouds/5.pcd")
+    clouds["background"] = lo.read_pcd(f"{REF}/assets/clouds/background.pcd")[::4].copy()
+    np.savez_compressed(os.path.join(HERE, "clouds.npz"), **clouds)
+
+    car = OnnxNet(f"{REF}/models/car.onnx")
+    armor = OnnxNet(f"{REF}/models/armor.onnx")
+    out = {}
+    for i in (0, 5):
+        img = cv2.imread(os.path.join(HERE, "frames", f"{i}.jpg"), cv2.IMREAD_COLOR)
+        tr = do.CascadeTrace()
+        robots = do.robot_detect(img, lambda x: car(x).numpy(), lambda x: armor(x).numpy(), trace=tr)
+        out[f"f{i}_cars"] = tr.car_dets
+        out[f"f{i}_rois"] = np.asarray(tr.rois, np.int32)
+        out[f"f{i}_armor_counts"] = np.asarray([len(a) for a in tr.armor_dets], np.int32)
+        out[f"f{i}_armors"] = np.concatenate(tr.armor_dets) if tr.armor_dets else np.zeros((0, 6), np.float32)
+        out[f"f{i}_robot_labels"] = np.asarray([r.label for r in robots if r.is_detected()], np.int32)
+        out[f"f{i}_robot_conf"] = np.asarray([r.confidence for r in robots if r.is_detected()], np.float32)
+        out[f"f{i}_robot_rects"] = np.asarray([r.rect for r in robots], np.float32)
+        print(i, "cars", len(tr.car_dets), "armors", out[f"f{i}_armor_counts"], "labels", out[f"f{i}_robot_labels"])
+        if i == 0:
+            # 1920x1080 variant of frame 0 (BASELINE config C2 geometry), resized with the oracle's resize
+            small = do.resize(img, 1920, 1080)
+            tr2 = do.CascadeTrace()
+            robots2 = do.robot_detect(small, lambda x: car(x).numpy(), lambda x: armor(x).numpy(), trace=tr2)
+            out["f0_1080_cars"] = tr2.car_dets
+            out["f0_1080_armor_counts"] = np.asarray([len(a) for a in tr2.armor_dets], np.int32)
+            out["f0_1080_armors"] = np.concatenate(tr2.armor_dets) if tr2.armor_dets else np.zeros((0, 6), np.float32)
+            out["f0_1080_robot_labels"] = np.asarray([r.label for r in robots2 if r.is_detected()], np.int32)
+            print("1080p cars", len(tr2.car_dets), "armors", out["f0_1080_armor_counts"], out["f0_1080_robot_labels"])
+    # locate: background (subsampled) then cloud 0, boxes = frame-0 cars
+    loc = lo.LocatorOracle(fx.IMAGE_SIZE[0], fx.IMAGE_SIZE[1], fx.INTRINSIC, fx.LIDAR_TO_CAMERA, fx.WORLD_TO_CAMERA)
+    loc.update(clouds["background"]); loc.update(clouds["c0"]); loc.cluster()
+    res = loc.search([tuple(c[:4]) for c in out["f0_cars"]])
+    out["f0_located"] = np.asarray([r is not None for r in res])
+    out["f0_locations"] = np.asarray([r if r is not None else (np.nan,) * 3 for r in res], np.float64)
+    out["f0_fg_clusters"] = np.asarray([len(loc.fg_points), loc.num_clusters], np.int32)
+    print("locate", out["f0_fg_clusters"], out["f0_locations"])
+    np.savez_compressed(os.path.join(HERE, "expected.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,147 @@
+"""GPU: detect path vs the oracle through the C ABI — preprocess bit-exact (u8 stage exact, fp16
+rounding of the /255 blob), network head output within fp16 tolerance of the fp32 ONNX oracle,
+final detections class-exact with IoU >= 0.99 (BASELINE north_star gate)."""
+import os
+
+import numpy as np
+import pytest
+
+import rm_radar_b200 as rr
+from oracle import detect_oracle as do
+from tests import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+
+needs_models = pytest.mark.skipif(not fx.have_models(), reason="engines / onnx copies not built")
+
+
+@pytest.fixture(scope="module")
+def robot_detector():
+    return rr.RobotDetector(fx.engine("car"), fx.engine("armor"), fx.IMAGE_SIZE, fx.CLASS_NUM, fx.MAX_BATCH, fx.OPT_BATCH)
+
+
+@pytest.fixture(scope="module")
+def oracle_nets():
+    from oracle.onnx_torch import OnnxNet
+    car, armor = OnnxNet(fx.onnx("car")), OnnxNet(fx.onnx("armor"))
+    return (lambda x: car(x).numpy()), (lambda x: armor(x).numpy())
+
+
+def fp16_blob(img, compat=True, border=None):
+    b, pp = do.preprocess(img, compat=compat, border_buf=border)
+    return b.astype(np.float16).astype(np.float32), pp
+
+
+@needs_models
+@pytest.mark.parametrize("size", [(1920, 1080), (1280, 1280), (2592, 2048), (810, 1080), (1280, 720), (57, 100),
+                                  (133, 178), (29, 44)])
+def test_preprocess_bit_exact(size):
+    """Letterbox kernel vs oracle for clean (1920x1080, 1280^2, the reference's bus/zidane sizes) and
+    bug-compatible 639-row / 639-column geometries, on a fresh detector (staging = zeros)."""
+    w, h = size
+    rng = np.random.default_rng(w * 7 + h)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    det = rr.Detector(fx.engine("car"), 1, (w, h), 1)
+    det.detect(img)
+    got = det.last_input(1)[0]
+    want, _ = fp16_blob(img)
+    assert np.array_equal(got, want), f"{np.sum(got != want)} of {got.size} input values differ"
+
+
+@needs_models
+def test_preprocess_corrected_mode_and_stale_staging():
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, (100, 57, 3), dtype=np.uint8)     # 639-column shear case
+    b = rng.integers(0, 256, (90, 61, 3), dtype=np.uint8)
+    det = rr.Detector(fx.engine("car"), 1, (64, 100), 1)
+    border = np.zeros(640 * 640 * 3, np.uint8)
+    for img in (a, b, a):       # stale bytes of the previous call must survive exactly like the reference buffer
+        det.detect(img)
+        want, _ = fp16_blob(img, border=border)
+        assert np.array_equal(det.last_input(1)[0], want)
+    det2 = rr.Detector(fx.engine("car"), 1, (64, 100), 1, compat=False)
+    det2.detect(a)
+    want, _ = fp16_blob(a, compat=False)
+    assert np.array_equal(det2.last_input(1)[0], want)
+
+
+@needs_models
+def test_network_output_vs_fp32_oracle(oracle_nets):
+    """Head output [1,5,34000] of the tcgen05 conv stack vs the fp32 ONNX graph on the golden frame.
+    fp16 operands / fp32 accumulate: SURVEY C.4 measured 0.009 px / 3e-4; gate at 0.25 px / 4e-3."""
+    car_net, _ = oracle_nets
+    img = fx.load_frame(0)
+    det = rr.Detector(fx.engine("car"), 1, fx.IMAGE_SIZE, 1)
+    dets = det.detect(img)
+    x, pp = do.preprocess(img)
+    ref = car_net(x[None])[0]
+    got = det.last_output(1)[0]
+    assert got.shape == ref.shape == (5, 34000)
+    hot = ref[4] > 0.05
+    assert np.abs(got[4] - ref[4]).max() < 4e-3
+    assert np.abs(got[:4, hot] - ref[:4, hot]).max() < 0.25
+    want = do.postprocess(ref, 1, pp, 0.65, 0.25)
+    fx.match_detections([d.as_array() for d in dets], want)
+
+
+@needs_models
+def test_cascade_golden_frames(robot_detector):
+    exp = np.load(os.path.join(fx.GOLDEN, "expected.npz"))
+    for f in (0, 5, 0):
+        img = fx.load_frame(f)
+        robots = robot_detector.detect(img)
+        cars = [d.as_array() for d in robot_detector.last_cars()]
+        fx.match_detections(cars, exp[f"f{f}_cars"])
+        counts = [len(robot_detector.last_armors(i)) for i in range(len(cars))]
+        assert counts == exp[f"f{f}_armor_counts"].tolist()
+        armors = [d.as_array() for i in range(len(cars)) for d in robot_detector.last_armors(i)]
+        fx.match_detections(armors, exp[f"f{f}_armors"], min_iou=0.99)
+        labels = [r.label for r in robots if r.isDetected()]
+        assert labels == exp[f"f{f}_robot_labels"].tolist()
+        conf = [r.confidence for r in robots if r.isDetected()]
+        assert np.allclose(conf, exp[f"f{f}_robot_conf"], atol=5e-3)
+        rects = np.array([r.rect for r in robots], np.float32)
+        for a, b in zip(rects, exp[f"f{f}_robot_rects"]):
+            assert fx.iou_xywh(a, b) >= 0.99
+        # output order: undetected robots in car order, then labelled ascending (detector.cpp:431-453)
+        det_flags = [r.isDetected() for r in robots]
+        assert det_flags == sorted(det_flags) and labels == sorted(labels)
+
+
+@needs_models
+def test_cascade_1080p_matches_live_oracle(robot_detector, oracle_nets):
+    """BASELINE config C2 geometry (1920x1080): CUDA path vs the oracle run live on the same frame."""
+    exp = np.load(os.path.join(fx.GOLDEN, "expected.npz"))
+    img = fx.resize_frame(fx.load_frame(0), 1920, 1080)
+    det = rr.RobotDetector(fx.engine("car"), fx.engine("armor"), (1920, 1080), fx.CLASS_NUM, fx.MAX_BATCH, fx.OPT_BATCH)
+    robots = det.detect(img)
+    cars = [d.as_array() for d in det.last_cars()]
+    fx.match_detections(cars, exp["f0_1080_cars"])
+    assert [len(det.last_armors(i)) for i in range(len(cars))] == exp["f0_1080_armor_counts"].tolist()
+    assert [r.label for r in robots if r.isDetected()] == exp["f0_1080_robot_labels"].tolist()
+    car_net, armor_net = oracle_nets
+    tr = do.CascadeTrace()
+    want = do.robot_detect(img, car_net, armor_net, trace=tr)
+    assert [r.label for r in want if r.is_detected()] == [r.label for r in robots if r.isDetected()]
+
+
+@needs_models
+def test_detector_batch_and_edge_cases():
+    det = rr.Detector(fx.engine("armor"), 12, (640, 640), 4, conf_thresh=0.5)
+    assert det.detect([]) == []
+    rng = np.random.default_rng(1)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for (w, h) in [(133, 178), (64, 64), (300, 200)]]
+    out = det.detect(imgs)
+    assert len(out) == 3 and all(isinstance(o, list) for o in out)
+    got = det.last_input(3)
+    border = [np.zeros(640 * 640 * 3, np.uint8) for _ in range(3)]
+    for i, im in enumerate(imgs):
+        want, _ = fp16_blob(im, border=border[i])
+        assert np.array_equal(got[i], want)
+    with pytest.raises(ValueError):
+        det.detect(imgs + imgs)            # batch > max_batch_size
+    with pytest.raises(ValueError):
+        rr.Detector(fx.engine("armor"), 3, (640, 640), 1)   # class count mismatch
+    # a black frame: no cars -> empty armor batch (the reference aborts inside TensorRT here, B#8)
+    rd = rr.RobotDetector(fx.engine("car"), fx.engine("armor"), (640, 480), 12, 20, 4)
+    assert rd.detect(np.zeros((480, 640, 3), np.uint8)) == []
