@@ -81,6 +81,9 @@ int rmr_detector_last_input(rmr_detector_t* d, float* out, int n_images);
 int rmr_detector_last_output(rmr_detector_t* d, float* out, int n_images);
 int rmr_detector_info(rmr_detector_t* d, int* anchors, int* classes, int* kernel_launches, double* flops_per_image);
 int rmr_detector_set_stream(rmr_detector_t* d, void* cuda_stream);
+/* bench: replays the network (the captured conv-stack graph) `iters` times at `batch` on the
+ * detector's stream, timed with CUDA events on that stream; ms = average per replay */
+int rmr_detector_time_forward(rmr_detector_t* d, int batch, int iters, float* ms);
 
 /* ---- radar::RobotDetector — src/detect/detector.h:171-190 ---------------------------------- */
 /* RobotDetector::RobotDetector(car_path, armor_path, image_size, armor_classes, max_cars, opt_cars,

@@ -171,6 +171,17 @@ class Detector:
     def set_stream(self, cuda_stream: int):
         _lib.check(self._lib.rmr_detector_set_stream(self._h, C.c_void_p(cuda_stream)))
 
+    def time_forward(self, batch: int, iters: int = 20) -> float:
+        """ms per replay of the conv-stack graph at `batch` (CUDA events on the detector's stream)."""
+        ms = C.c_float()
+        _lib.check(self._lib.rmr_detector_time_forward(self._h, batch, iters, C.byref(ms)))
+        return ms.value
+
+    def info(self):
+        a, c, k, f = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        _lib.check(self._lib.rmr_detector_info(self._h, C.byref(a), C.byref(c), C.byref(k), C.byref(f)))
+        return dict(anchors=a.value, classes=c.value, kernel_launches=k.value, flops_per_image=f.value)
+
 
 class _DetectorView(Detector):
     def __init__(self, lib, handle, classes, input_size):   # borrowed handle: never destroyed

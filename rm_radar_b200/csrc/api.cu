@@ -123,6 +123,27 @@ int rmr_detector_info(rmr_detector_t* d, int* anchors, int* classes, int* kernel
 int rmr_detector_set_stream(rmr_detector_t* d, void* cuda_stream) {
     return guarded([&] { d->impl->set_stream(static_cast<cudaStream_t>(cuda_stream)); });
 }
+int rmr_detector_time_forward(rmr_detector_t* d, int batch, int iters, float* ms) {
+    return guarded([&] {
+        if (!d || !ms || iters <= 0) throw std::invalid_argument("bad argument");
+        RMR_CUDA(cudaSetDevice(d->impl->device()));
+        cudaStream_t s = d->impl->stream();
+        d->impl->net().forward(batch, s);   // warm-up + graph capture
+        d->impl->net().forward(batch, s);
+        cudaEvent_t e0, e1;
+        RMR_CUDA(cudaEventCreate(&e0));
+        RMR_CUDA(cudaEventCreate(&e1));
+        RMR_CUDA(cudaEventRecord(e0, s));
+        for (int i = 0; i < iters; ++i) d->impl->net().forward(batch, s);
+        RMR_CUDA(cudaEventRecord(e1, s));
+        RMR_CUDA(cudaEventSynchronize(e1));
+        float t = 0.f;
+        RMR_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        *ms = t / iters;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    });
+}
 
 // ---------------------------------------------------------------- RobotDetector
 int rmr_robot_detector_create(rmr_robot_detector_t** out, const char* car_engine, const char* armor_engine,

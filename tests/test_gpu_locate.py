@@ -125,12 +125,13 @@ def test_edge_cases():
     # size filter + ordering + the unclustered (-1) group, as in tests/test_oracle_locate.py
     dev, ora = pair(200, 200, I3, I4, I4, zoom_factor=1.0, cluster_tolerance=2.0, min_cluster_size=3,
                     max_cluster_size=6, min_depth_diff=1, max_depth_diff=10)
+
     def cloud_from_pixels(pix, depth):
         return np.array([[(u + 0.5) * depth, (v + 0.5) * depth, depth] for (u, v) in pix], np.float32)
     fg = [(u, 10) for u in range(10, 13)] + [(u, 50) for u in range(10, 15)] + [(u, 90) for u in range(10, 18)] + \
          [(10, 130)] + [(u, 150) for u in range(10, 13)]
     bgc = cloud_from_pixels(fg, 9.0)
-    frc = cloud_from_pixels(fg, 5.0)
+    frc = cloud_from_pixels(fg, 1.0)     # depth 1: neighbouring pixels are 1 unit apart (< tolerance 2)
     for c in (bgc, frc):
         dev.update(c); ora.update(c)
     dev.cluster(); ora.cluster()
