@@ -168,7 +168,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     frame, bg, cloud, fx = make_inputs(1 + rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)   # a capturable, non-legacy stream shared by detector + locator
+    torch.cuda.set_stream(stream)
     det = rr.RobotDetector(fx.engine("car"), fx.engine("armor"), (W, H), fx.CLASS_NUM, fx.MAX_BATCH, fx.OPT_BATCH,
                            device=local_rank)
     loc = rr.Locator(W, H, fx.scaled_intrinsic(W, H), fx.LIDAR_TO_CAMERA, fx.WORLD_TO_CAMERA, device=local_rank)

@@ -149,16 +149,27 @@ void Net::forward(int batch, cudaStream_t s) {
     }
     if (bp.graph == nullptr) {
         conv_init();
+        // capture on a private stream: the caller's stream may be the legacy default stream, which
+        // cannot be captured, and nothing executes during capture anyway
+        cudaStream_t cs = nullptr;
+        RMR_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         cudaGraph_t g = nullptr;
-        RMR_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) {
+            cudaStreamDestroy(cs);
+            RMR_CUDA(e);
+        }
         try {
-            run_steps(bp, batch, s);
+            run_steps(bp, batch, cs);
         } catch (...) {
-            cudaStreamEndCapture(s, &g);
+            cudaStreamEndCapture(cs, &g);
             if (g) cudaGraphDestroy(g);
+            cudaStreamDestroy(cs);
             throw;
         }
-        RMR_CUDA(cudaStreamEndCapture(s, &g));
+        e = cudaStreamEndCapture(cs, &g);
+        cudaStreamDestroy(cs);
+        RMR_CUDA(e);
         RMR_CUDA(cudaGraphInstantiate(&bp.graph, g, 0));
         cudaGraphDestroy(g);
     }

@@ -1,0 +1,74 @@
+// C++ host test of include/radar.hpp: drives the reference-shaped classes the way
+// SampleRadar::runOnce does (/root/reference/samples/sample_radar.h:106-127: Locator::update + cluster,
+// RobotDetector::detect, Locator::search) and prints one JSON document that tests/test_gpu_cpp_host.py
+// compares with the oracle.  Inputs are raw files written by the test (no OpenCV / PCL needed):
+//   radar_hpp_test car.rmeng armor.rmeng frame.bgr W H background.f32 cloud.f32
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <vector>
+
+#include "radar.hpp"
+
+namespace {
+std::vector<char> slurp(const char* path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) {
+        std::fprintf(stderr, "cannot open %s\n", path);
+        std::exit(2);
+    }
+    return std::vector<char>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+}  // namespace
+
+int main(int argc, char** argv) {
+    if (argc != 8) {
+        std::fprintf(stderr, "usage: %s car.rmeng armor.rmeng frame.bgr W H background.f32 cloud.f32\n", argv[0]);
+        return 2;
+    }
+    const int W = std::atoi(argv[4]), H = std::atoi(argv[5]);
+    const std::vector<char> frame = slurp(argv[3]), bg = slurp(argv[6]), cloud = slurp(argv[7]);
+    if (frame.size() != static_cast<size_t>(W) * H * 3) {
+        std::fprintf(stderr, "frame size mismatch\n");
+        return 2;
+    }
+    // calibration of the sample (samples/main.cpp:12-21)
+    const radar::Matx33f K{1685.51538398561f, 0, 1278.99324114319f, 0, 1685.26471848220f, 1037.21273138299f, 0, 0, 1};
+    const radar::Matx44f L2C{0, -1, 0, 0.85443f, 0, 0, -1, -37.6845f, 1, 0, 0, 12.2631f, 0, 0, 0, 1};
+    const radar::Matx44f W2C{0.05975021f, 0.99807031f, 0.01689906f, -7179.65399136f, 0.28962566f, -0.00113262f,
+                             -0.95713933f, -4671.34956587f, -0.9552732f, 0.06208368f, -0.28913445f, 28286.8920291f,
+                             0, 0, 0, 1};
+    // constructor failures throw (detector.cpp:80): a missing engine must surface as invalid_argument
+    bool threw = false;
+    try {
+        radar::Detector bad("/nonexistent/model.rmeng", 1, radar::Size{W, H}, 1);
+    } catch (const std::invalid_argument&) {
+        threw = true;
+    }
+    radar::RobotDetector detector(argv[1], argv[2], radar::Size{W, H}, 12, 20, 4);   // sample_radar.h:32-34
+    radar::Locator locator(W, H, K, L2C, W2C);
+    locator.update(radar::CloudView{reinterpret_cast<const float*>(bg.data()), static_cast<int>(bg.size() / 12), 12});
+    locator.update(radar::CloudView{reinterpret_cast<const float*>(cloud.data()), static_cast<int>(cloud.size() / 12), 12});
+    locator.cluster();
+    std::vector<radar::Robot> robots =
+        detector.detect(radar::ImageView{reinterpret_cast<const unsigned char*>(frame.data()), W, H, W * 3});
+    locator.search(robots);
+
+    std::printf("{\"ctor_throws\": %s, \"robots\": [", threw ? "true" : "false");
+    for (size_t i = 0; i < robots.size(); ++i) {
+        const radar::Robot& r = robots[i];
+        const auto rf = r.rectf().value();
+        const auto ri = r.rect().value();
+        std::printf("%s{\"rect\": [%.9g, %.9g, %.9g, %.9g], \"rect_int\": [%d, %d, %d, %d], \"label\": %d, "
+                    "\"confidence\": %.9g, \"n_armors\": %d, \"located\": %s, \"location\": [%.9g, %.9g, %.9g]}",
+                    i ? ", " : "", rf.x, rf.y, rf.width, rf.height, ri.x, ri.y, ri.width, ri.height,
+                    r.label().value_or(-1), r.confidence().value_or(0.f),
+                    r.isDetected() ? static_cast<int>(r.armors()->size()) : -1, r.isLocated() ? "true" : "false",
+                    r.isLocated() ? r.location()->x : 0.f, r.isLocated() ? r.location()->y : 0.f,
+                    r.isLocated() ? r.location()->z : 0.f);
+    }
+    std::printf("]}\n");
+    if (!robots.empty()) std::cerr << robots[0] << std::endl;   // operator<< compiles and runs
+    return 0;
+}

@@ -67,3 +67,19 @@ def test_no_cpu_fallback_errors_loudly():
         rr.Locator(640, 480, np.eye(3), np.eye(4), np.eye(4))
     with pytest.raises(ValueError):
         rr.Detector("/nonexistent/model.engine", 1, (640, 480), 1)
+
+
+def test_headers_compile_standalone(tmp_path):
+    """rm_radar_b200.h is plain C (what cgo / JNI / ctypes bind); radar.hpp is C++20 and needs neither
+    OpenCV nor PCL.  Syntax-only: no library or GPU required."""
+    import shutil
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    if shutil.which("gcc") is None or shutil.which("g++") is None:
+        pytest.skip("no host compiler")
+    c = tmp_path / "t.c"
+    c.write_text('#include "rm_radar_b200.h"\nint main(void){ rmr_robot_t r; (void)r; return sizeof(rmr_detection_t) != 24; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I" + inc, str(c)])
+    cpp = tmp_path / "t.cpp"
+    cpp.write_text('#include "radar.hpp"\nint main(){ radar::Robot r; return r.isDetected() || r.isLocated(); }\n')
+    subprocess.check_call(["g++", "-std=c++20", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I" + inc, str(cpp)])
