@@ -84,6 +84,10 @@ int rmr_detector_set_stream(rmr_detector_t* d, void* cuda_stream);
 /* bench: replays the network (the captured conv-stack graph) `iters` times at `batch` on the
  * detector's stream, timed with CUDA events on that stream; ms = average per replay */
 int rmr_detector_time_forward(rmr_detector_t* d, int batch, int iters, float* ms);
+/* bench / profiling: per-op table of the engine plan at `batch`.  Each row of `rows` is 12 doubles:
+ * type (0 conv, 1 maxpool5, 2 upsample2, 3 copy), tcgen05 path used (0/1), h_in, w_in, cin, h_out, w_out,
+ * cout, k, stride, flops (2*MAC, conv only), ms per launch (CUDA events, `iters` back-to-back launches). */
+int rmr_detector_profile_ops(rmr_detector_t* d, int batch, int iters, double* rows, int capacity, int* n_ops);
 
 /* ---- radar::RobotDetector — src/detect/detector.h:171-190 ---------------------------------- */
 /* RobotDetector::RobotDetector(car_path, armor_path, image_size, armor_classes, max_cars, opt_cars,
@@ -138,6 +142,11 @@ int rmr_locator_read_foreground(rmr_locator_t* l, float* xyz_pix, int capacity);
  * returns the max abs difference; also times the tcgen05 kernel (ms per launch over `iters`). */
 int rmr_conv_selftest(int n, int h_in, int w_in, int cin, int cout, int k, int stride, int act, int residual,
                       int out_f32, unsigned seed, int iters, float* max_abs_diff, float* max_ref, float* ms);
+
+/* profiling aid (tests/bench only): per-CTA clock64 timeline of one tcgen05 conv launch, 64 slots per CTA
+ * (slot map in csrc/conv.cu); `out` holds capacity_ctas * 64 int64 */
+int rmr_conv_timeline(int n, int h_in, int w_in, int cin, int cout, int k, int stride, long long* out,
+                      int capacity_ctas, int* n_ctas);
 
 #ifdef __cplusplus
 }

@@ -177,6 +177,16 @@ class Detector:
         _lib.check(self._lib.rmr_detector_time_forward(self._h, batch, iters, C.byref(ms)))
         return ms.value
 
+    def profile_ops(self, batch: int = 1, iters: int = 20):
+        """Per-op table of the engine plan: list of dicts (type, umma, shapes, flops, ms)."""
+        cap = 512
+        rows = np.zeros((cap, 12), np.float64)
+        n = C.c_int()
+        _lib.check(self._lib.rmr_detector_profile_ops(self._h, batch, iters,
+                                                      rows.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(n)))
+        keys = ("type", "umma", "h_in", "w_in", "cin", "h_out", "w_out", "cout", "k", "stride", "flops", "ms")
+        return [dict(zip(keys, rows[i].tolist())) for i in range(min(n.value, cap))]
+
     def info(self):
         a, c, k, f = C.c_int(), C.c_int(), C.c_int(), C.c_double()
         _lib.check(self._lib.rmr_detector_info(self._h, C.byref(a), C.byref(c), C.byref(k), C.byref(f)))
@@ -367,3 +377,12 @@ def conv_selftest(n, h, w, cin, cout, k, stride, act=1, residual=0, out_f32=0, s
     _lib.check(lib.rmr_conv_selftest(n, h, w, cin, cout, k, stride, act, residual, out_f32, seed, iters,
                                      C.byref(d), C.byref(r), C.byref(ms)))
     return d.value, r.value, ms.value
+
+
+def conv_timeline(n, h, w, cin, cout, k, stride, max_ctas=4096):
+    """Per-CTA clock64 timeline of one tcgen05 conv launch: int64 array [ctas, 64] (profiling aid)."""
+    lib = _lib.load()
+    out = np.zeros((max_ctas, 64), np.int64)
+    nc = C.c_int()
+    _lib.check(lib.rmr_conv_timeline(n, h, w, cin, cout, k, stride, out.ctypes.data, max_ctas, C.byref(nc)))
+    return out[:min(nc.value, max_ctas)]

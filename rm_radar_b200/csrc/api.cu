@@ -145,6 +145,26 @@ int rmr_detector_time_forward(rmr_detector_t* d, int batch, int iters, float* ms
     });
 }
 
+int rmr_detector_profile_ops(rmr_detector_t* d, int batch, int iters, double* rows, int capacity, int* n_ops) {
+    return guarded([&] {
+        if (!d || !rows || !n_ops) throw std::invalid_argument("null argument");
+        RMR_CUDA(cudaSetDevice(d->impl->device()));
+        Net& net = d->impl->net();
+        const std::vector<float> ms = net.profile_ops(batch, iters, d->impl->stream());
+        const auto& ops = net.ops();
+        *n_ops = static_cast<int>(ops.size());
+        for (int i = 0; i < *n_ops && i < capacity; ++i) {
+            const EngineOp& op = ops[i];
+            double* r = rows + static_cast<size_t>(i) * 12;
+            r[0] = op.type; r[1] = net.op_uses_umma(batch, i) ? 1 : 0;
+            r[2] = op.src_h; r[3] = op.src_w; r[4] = op.src_c; r[5] = op.dst_h; r[6] = op.dst_w; r[7] = op.dst_c;
+            r[8] = op.k; r[9] = op.stride;
+            r[10] = op.type == 0 ? 2.0 * batch * op.dst_h * op.dst_w * static_cast<double>(op.dst_c) * op.k * op.k * op.src_c : 0.0;
+            r[11] = ms[i];
+        }
+    });
+}
+
 // ---------------------------------------------------------------- RobotDetector
 int rmr_robot_detector_create(rmr_robot_detector_t** out, const char* car_engine, const char* armor_engine,
                               int image_width, int image_height, int armor_classes, int max_cars, float iou_thresh,
@@ -411,6 +431,47 @@ int rmr_conv_selftest(int n, int h_in, int w_in, int cin, int cout, int k, int s
         }
         cudaStreamDestroy(s);
         cudaFree(d_in); cudaFree(d_w); cudaFree(d_res); cudaFree(d_bias); cudaFree(d_out_a); cudaFree(d_out_b);
+    });
+}
+
+int rmr_conv_timeline(int n, int h_in, int w_in, int cin, int cout, int k, int stride, long long* out,
+                      int capacity_ctas, int* n_ctas) {
+    return guarded([&] {
+        const int pad = k / 2;
+        const int h_out = (h_in + 2 * pad - k) / stride + 1, w_out = (w_in + 2 * pad - k) / stride + 1;
+        const int cout_pad = (cout + 15) / 16 * 16;
+        const size_t in_elems = static_cast<size_t>(n) * h_in * w_in * cin;
+        const size_t out_elems = static_cast<size_t>(n) * h_out * w_out * cout_pad;
+        const size_t w_elems = static_cast<size_t>(cout_pad) * k * k * cin;
+        __half *d_in, *d_w, *d_out;
+        float* d_bias;
+        RMR_CUDA(cudaMalloc(&d_in, in_elems * 2));
+        RMR_CUDA(cudaMalloc(&d_w, w_elems * 2));
+        RMR_CUDA(cudaMalloc(&d_out, out_elems * 2));
+        RMR_CUDA(cudaMalloc(&d_bias, cout_pad * 4));
+        RMR_CUDA(cudaMemset(d_in, 0, in_elems * 2));
+        RMR_CUDA(cudaMemset(d_w, 0, w_elems * 2));
+        RMR_CUDA(cudaMemset(d_bias, 0, cout_pad * 4));
+        ConvDesc d;
+        d.in = d_in; d.in_pitch = cin; d.in_coff = 0; d.cin = cin; d.h_in = h_in; d.w_in = w_in;
+        d.out = d_out; d.out_pitch = cout_pad; d.out_coff = 0; d.cout = cout; d.out_f32 = 0;
+        d.h_out = h_out; d.w_out = w_out; d.k = k; d.stride = stride; d.act = 1;
+        d.w = d_w; d.bias = d_bias; d.cout_pad = cout_pad; d.cin_pad = cin; d.n = n;
+        ConvLaunch l = make_conv_launch(d);
+        const int ctas = static_cast<int>(l.grid.x * l.grid.y);
+        long long* d_dbg;
+        RMR_CUDA(cudaMalloc(&d_dbg, sizeof(long long) * 64 * ctas));
+        RMR_CUDA(cudaMemset(d_dbg, 0, sizeof(long long) * 64 * ctas));
+        cudaStream_t s;
+        RMR_CUDA(cudaStreamCreate(&s));
+        for (int i = 0; i < 3; ++i) launch_conv_umma(l, s);
+        l.p.dbg = d_dbg;
+        launch_conv_umma(l, s);
+        RMR_CUDA(cudaStreamSynchronize(s));
+        *n_ctas = ctas;
+        RMR_CUDA(cudaMemcpy(out, d_dbg, sizeof(long long) * 64 * std::min(ctas, capacity_ctas), cudaMemcpyDeviceToHost));
+        cudaStreamDestroy(s);
+        cudaFree(d_in); cudaFree(d_w); cudaFree(d_out); cudaFree(d_bias); cudaFree(d_dbg);
     });
 }
 

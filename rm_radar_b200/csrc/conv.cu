@@ -18,6 +18,7 @@
 #include "conv.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -25,19 +26,46 @@ namespace rmr {
 
 namespace {
 
-constexpr int kStages = 5;
-constexpr int kStageBytes = 32768;   // 16 KB A (128 x 64 fp16) + 16 KB B (<=128 x 64 fp16)
+constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
-constexpr int kTmemCols = 128;
+constexpr int kSmemBudget = 100 * 1024;   // operand ring per CTA: two CTAs co-reside on one SM
 
-__global__ void __launch_bounds__(kThreads, 1)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// programmatic dependent launch: the next layer's prologue (barrier init, TMEM alloc, bias + weight
+// loads) overlaps this layer's tail; activations are only touched after pdl_wait()
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float exp2f_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-5 = epilogue.
+// Producer and issuer run warp-converged (one elected lane issues) so that the loop bookkeeping
+// stays in the uniform datapath; two CTAs per SM let one CTA's epilogue hide behind the other's
+// main loop.
+__global__ void __launch_bounds__(kThreads, 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[kStages];
-    __shared__ __align__(8) uint64_t bar_empty[kStages];
+    __shared__ __align__(8) uint64_t bar_full[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
     __shared__ __align__(8) uint64_t bar_acc;
     __shared__ uint32_t tmem_base_slot;
+    __shared__ int4 s_tap[9];
+    __shared__ float s_bias[128];
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5;
@@ -51,14 +79,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int tile_n = mt / p.tiles_h;
     const int ow0 = tile_w * p.tw, oh0 = tile_h * p.th, n0 = tile_n * p.tn;
     const int ch0 = blockIdx.y * p.block_n;   // first output channel of this CTA
+    long long* dbg = p.dbg ? p.dbg + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tm_a);
-        tma_prefetch_desc(&tm_b);
-    }
-    if (warp == 1) {
+    // ---- setup: nothing here reads activations, so under PDL it overlaps the previous layer ----
+    if (warp == 0) {
         if (lane == 0) {
-            for (int i = 0; i < kStages; ++i) {
+            tma_prefetch_desc(&tm_a);
+            tma_prefetch_desc(&tm_b);
+        }
+        if (lane < p.ntaps) s_tap[lane] = p.tap[lane];
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < p.stages; ++i) {
                 mbar_init(smem_u32(&bar_full[i]), 1);
                 mbar_init(smem_u32(&bar_empty[i]), 1);
             }
@@ -66,55 +99,88 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
+        tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
         tmem_relinquish();
+    } else {
+        const int t = threadIdx.x - 64;
+        if (t < p.block_n) s_bias[t] = __ldg(p.bias + ch0 + t);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    pdl_launch_dependents();
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
     const int num_it = p.ntaps * p.kpt;
-    const uint32_t a_bytes = 128u * p.bk * 2u;
-    const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * p.bk * 2u;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int it = 0; it < num_it; ++it) {
-                const int tap = it / p.kpt;
-                const int kc = it - tap * p.kpt;
-                const int4 t = p.tap[tap];
-                mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+        // ------------------------------ TMA producer ------------------------------
+        const bool leader = elect_one();
+        const uint32_t tx = p.a_bytes + p.b_bytes;
+        const int npre = min(p.stages, num_it);
+        // weights are constants: the first ring pass of B tiles goes out before the grid dependency resolves
+        if (leader) {
+            for (int i = 0; i < npre; ++i) {
+                const uint32_t full = smem_u32(&bar_full[i]);
+                mbar_expect_tx(full, tx);
+                tma_load_2d(smem_base + i * p.stage_stride + p.b_off, &tm_b, full, i * p.bk, ch0);
+            }
+        }
+        pdl_wait();
+        int stage = 0, it = 0;
+        uint32_t phase = 0;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+            const int4 t = s_tap[tap];
+            const int cw = ow0 + t.y, chh = oh0 + t.w;
+            int cc = p.cin_coff + t.x;
+            for (int kc = 0; kc < p.kpt; ++kc, ++it, cc += p.bk) {
                 const uint32_t full = smem_u32(&bar_full[stage]);
-                mbar_expect_tx(full, a_bytes + b_bytes);
-                const uint32_t sa = smem_base + stage * kStageBytes;
-                tma_load_5d(sa, &tm_a, full, p.cin_coff + t.x + kc * p.bk, ow0 + t.y, t.z, oh0 + t.w, n0);
-                tma_load_2d(sa + 16384, &tm_b, full, tap * p.cin + kc * p.bk, ch0);
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                const uint32_t sa = smem_base + stage * p.stage_stride;
+                if (it >= npre) {
+                    mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                    if (leader) {
+                        mbar_expect_tx(full, tx);
+                        tma_load_2d(sa + p.b_off, &tm_b, full, it * p.bk, ch0);
+                    }
+                }
+                if (leader) {
+                    if (dbg && it < 16) dbg[24 + it] = clock64();
+                    tma_load_5d(sa, &tm_a, full, cc, cw, t.z, chh, n0);
+                }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const int ksteps = p.bk / 16;
-            for (int it = 0; it < num_it; ++it) {
-                mbar_wait(smem_u32(&bar_full[stage]), phase);
-                tc_fence_after();
-                const uint32_t sa = smem_base + stage * kStageBytes;
-                const uint64_t adesc = umma_smem_desc(sa, p.sbo, p.layout);
-                const uint64_t bdesc = umma_smem_desc(sa + 16384, p.sbo, p.layout);
-                for (int k = 0; k < ksteps; ++k) {
-                    // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field
-                    umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, p.idesc, (it | k) != 0);
-                }
+        // ------------------------------ MMA issuer ------------------------------
+        const bool leader = elect_one();
+        const uint64_t adesc0 = umma_smem_desc(smem_base, p.sbo, p.layout);
+        const uint64_t bdesc0 = umma_smem_desc(smem_base + p.b_off, p.sbo, p.layout);
+        const uint32_t stage_step = p.stage_stride >> 4;   // descriptor start-address units (16 B)
+        const int ksteps = p.bk >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < num_it; ++it) {
+            mbar_wait(smem_u32(&bar_full[stage]), phase);
+            tc_fence_after();
+            if (leader) {
+                if (dbg && it < 16) dbg[2 + it] = clock64();
+                const uint64_t ad = adesc0 + static_cast<uint64_t>(stage * stage_step);
+                const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * stage_step);
+                // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+                for (int k = 0; k < ksteps; ++k)
+                    umma_f16(tmem_base, ad + 2u * k, bd + 2u * k, p.idesc, (it | k) != 0);
                 umma_commit(smem_u32(&bar_empty[stage]));   // frees the smem slot when the MMAs retire
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
-            umma_commit(smem_u32(&bar_acc));                // accumulator complete
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        if (leader) {
+            umma_commit(smem_u32(&bar_acc));                // accumulator complete
+            if (dbg) dbg[18] = clock64();
+        }
+        __syncwarp();
     } else {
         // ---------------- epilogue: 4 warps, one TMEM lane quarter each ----------------
         const int q = warp & 3;
@@ -126,78 +192,121 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const bool valid = (ow < p.w_out) && (oh < p.h_out) && (n < p.n);
         const size_t pix = (static_cast<size_t>(n) * p.h_out + oh) * p.w_out + ow;
         const int nvalid = min(p.block_n, p.cout - ch0);   // real output channels in this tile
+        const __half* rptr = (p.res != nullptr && valid) ? p.res + pix * p.res_pitch + p.res_coff + ch0 : nullptr;
+        const bool vec = p.vec_ok != 0;
 
-        mbar_wait(smem_u32(&bar_acc), 0);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-            uint32_t v[16];
-            __syncwarp();
-            tmem_ld_16(taddr + c0, v);
-            tmem_ld_wait();
-            if (valid && c0 < nvalid) {
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float x = __uint_as_float(v[j]) + __ldg(p.bias + ch0 + c0 + j);
-                if (p.act) x = __fdividef(x, 1.0f + __expf(-x));
-                f[j] = x;
-            }
-            const int cnt = min(16, nvalid - c0);
-            if (p.res != nullptr) {
-                const __half* r = p.res + pix * p.res_pitch + p.res_coff + ch0 + c0;
-                if (cnt == 16) {
-                    const uint4 r0 = *reinterpret_cast<const uint4*>(r);
-                    const uint4 r1 = *reinterpret_cast<const uint4*>(r + 8);
-                    const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
-                    const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 a = __half22float2(h0[j]);
-                        const float2 b = __half22float2(h1[j]);
-                        f[2 * j] += a.x; f[2 * j + 1] += a.y;
-                        f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
-                    }
-                } else {
-                    for (int j = 0; j < cnt; ++j) f[j] += __half2float(r[j]);
+        pdl_wait();   // residual reads and output writes must follow the previous grid
+        uint4 rnext[4];
+        auto fetch_res = [&](int c0) {
+            const int cnt = nvalid - c0;
+            if (rptr != nullptr && vec && cnt >= 16) {
+                rnext[0] = *reinterpret_cast<const uint4*>(rptr + c0);
+                rnext[1] = *reinterpret_cast<const uint4*>(rptr + c0 + 8);
+                if (cnt >= 32) {
+                    rnext[2] = *reinterpret_cast<const uint4*>(rptr + c0 + 16);
+                    rnext[3] = *reinterpret_cast<const uint4*>(rptr + c0 + 24);
                 }
             }
+        };
+        fetch_res(0);
+
+        mbar_wait(smem_u32(&bar_acc), 0);
+        if (dbg && threadIdx.x == 64) dbg[19] = clock64();
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        for (int c0 = 0; c0 < nvalid; c0 += 32) {
+            uint32_t v[32];
+            __syncwarp();   // tcgen05.ld is warp-aligned: reconverge after the predicated stores
+            tmem_ld_32(taddr + c0, v);
+            uint4 rcur[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+            if (c0 + 32 < nvalid) fetch_res(c0 + 32);
+            tmem_ld_wait();
+            if (dbg && threadIdx.x == 64 && c0 == 0) dbg[40] = clock64();
+            if (valid) {
+            const int cnt = min(32, nvalid - c0);
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
+            if (p.act) {
+                // SiLU, staged so that the 32 independent MUFU chains pipeline (ex2 pass, then rcp pass)
+                float e[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) e[j] = 1.0f + exp2f_approx(-1.4426950408889634f * f[j]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = f[j] * rcp_approx(e[j]);
+            }
+            if (rptr != nullptr) {
+                if (vec && cnt >= 16) {
+                    const __half2* h = reinterpret_cast<const __half2*>(rcur);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float2 a = __half22float2(h[j]);
+                        f[2 * j] += a.x; f[2 * j + 1] += a.y;
+                    }
+                    if (cnt >= 32) {
+#pragma unroll
+                        for (int j = 8; j < 16; ++j) {
+                            const float2 a = __half22float2(h[j]);
+                            f[2 * j] += a.x; f[2 * j + 1] += a.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 16; j < 32; ++j)
+                            if (j < cnt) f[j] += __half2float(rptr[c0 + j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < cnt) f[j] += __half2float(rptr[c0 + j]);
+                }
+            }
+            if (dbg && threadIdx.x == 64 && c0 == 0) dbg[41] = clock64() + (__float_as_int(f[0]) & 0);
             if (p.out_f32) {
                 float* o = static_cast<float*>(p.out) + pix * p.out_pitch + p.out_coff + ch0 + c0;
-                if (cnt == 16) {
+                if (vec && (cnt & 3) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    for (int j = 0; j < 8; ++j)
+                        if (4 * j < cnt)
+                            reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                 } else {
-                    for (int j = 0; j < cnt; ++j) o[j] = f[j];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < cnt) o[j] = f[j];
                 }
             } else {
                 __half* o = static_cast<__half*>(p.out) + pix * p.out_pitch + p.out_coff + ch0 + c0;
-                if (cnt == 16) {
-                    uint4 w0, w1;
-                    __half2* h0 = reinterpret_cast<__half2*>(&w0);
-                    __half2* h1 = reinterpret_cast<__half2*>(&w1);
+                if (vec && (cnt & 7) == 0) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        h0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-                        h1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+                        if (8 * j < cnt) {
+                            uint4 w;
+                            __half2* h = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(f[8 * j + 2 * u], f[8 * j + 2 * u + 1]);
+                            reinterpret_cast<uint4*>(o)[j] = w;
+                        }
                     }
-                    reinterpret_cast<uint4*>(o)[0] = w0;
-                    reinterpret_cast<uint4*>(o)[1] = w1;
                 } else {
-                    for (int j = 0; j < cnt; ++j) o[j] = __float2half_rn(f[j]);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < cnt) o[j] = __float2half_rn(f[j]);
                 }
             }
             }
+            if (dbg && threadIdx.x == 64 && c0 == 0) dbg[42] = clock64();
         }
         __syncwarp();
+        if (dbg && threadIdx.x == 64) dbg[20] = clock64();
     }
 
     tc_fence_before();
     __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[21] = clock64();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc(tmem_base, p.tmem_cols);
     }
 }
 
@@ -389,11 +498,18 @@ void encode(CUtensorMap* tm, void* base, int rank, const cuuint64_t* dims, const
     if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
 }
 
-int pick_block_n(int cout_pad) {
-    if (cout_pad <= 128) return cout_pad;
-    for (int bn = 128; bn >= 16; bn -= 16)
-        if (cout_pad % bn == 0) return bn;
-    return 16;
+// Output-channel tile: the widest divisor of cout_pad (multiple of 16, <= 128) that still yields at
+// least one CTA per SM; small feature maps take narrower tiles (more CTAs, shorter epilogues).
+int pick_block_n(int cout_pad, long m_tiles) {
+    int best = 0;
+    for (int bn = 128; bn >= 16; bn -= 16) {
+        if (cout_pad % bn != 0) continue;
+        if (best == 0) best = bn;
+        if (bn < 32 && best >= 32) break;
+        best = bn;
+        if (m_tiles * (cout_pad / bn) >= 148) break;
+    }
+    return best;
 }
 
 }  // namespace
@@ -412,7 +528,6 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
     std::memset(&l, 0, sizeof(l));
     ConvParams& p = l.p;
     p.n = d.n; p.h_out = d.h_out; p.w_out = d.w_out; p.cout = d.cout;
-    p.block_n = pick_block_n(d.cout_pad);
     p.bk = (d.cin % 64 == 0) ? 64 : 32;
     p.kpt = d.cin / p.bk;
     p.ntaps = d.k * d.k;
@@ -432,6 +547,17 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
     p.tiles_w = (d.w_out + p.tw - 1) / p.tw;
     p.tiles_h = (d.h_out + p.th - 1) / p.th;
     p.tiles_n = (d.n + p.tn - 1) / p.tn;
+    p.block_n = pick_block_n(d.cout_pad, static_cast<long>(p.tiles_w) * p.tiles_h * p.tiles_n);
+    // operand ring: A = 128 pixel rows x BK, B = block_n rows x BK (both multiples of 1 KB)
+    p.a_bytes = 128u * p.bk * 2u;
+    p.b_bytes = static_cast<uint32_t>(p.block_n) * p.bk * 2u;
+    p.b_off = p.a_bytes;
+    p.stage_stride = p.a_bytes + p.b_bytes;
+    p.stages = std::max(1, std::min({kMaxStages, static_cast<int>(kSmemBudget / p.stage_stride), p.ntaps * p.kpt}));
+    p.tmem_cols = p.block_n <= 32 ? 32u : p.block_n <= 64 ? 64u : 128u;
+    const int out_align = d.out_f32 ? 4 : 8;
+    p.vec_ok = (d.out_pitch % out_align == 0 && d.out_coff % out_align == 0 &&
+                (d.res == nullptr || (d.res_pitch % 8 == 0 && d.res_coff % 8 == 0))) ? 1 : 0;
     const int S = d.stride;
     for (int r = 0; r < d.k; ++r)
         for (int s = 0; s < d.k; ++s) {
@@ -470,24 +596,39 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
         encode(&l.tm_b, const_cast<__half*>(d.w), 2, dims, strides, box, swz);
     }
     l.grid = dim3(p.tiles_w * p.tiles_h * p.tiles_n, d.cout_pad / p.block_n, 1);
-    l.smem_bytes = kStages * kStageBytes + 1024;
+    l.smem_bytes = p.stages * static_cast<int>(p.stage_stride) + 1024;
     l.flops = 2.0 * d.n * d.h_out * d.w_out * static_cast<double>(d.cout) * d.k * d.k * d.cin;
     return l;
 }
+
+static bool g_use_pdl = true;
 
 void conv_init() {
     static std::once_flag once;
     std::call_once(once, [] {
         RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kStages * kStageBytes + 1024));
+                                      kSmemBudget + 1024));
+        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
         get_encode_fn();
+        const char* e = std::getenv("RMR_NO_PDL");
+        g_use_pdl = !(e && e[0] == '1');
     });
 }
 
 void launch_conv_umma(const ConvLaunch& l, cudaStream_t s) {
     conv_init();
-    conv_umma_kernel<<<l.grid, kThreads, l.smem_bytes, s>>>(l.tm_a, l.tm_b, l.p);
-    RMR_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = l.grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = static_cast<size_t>(l.smem_bytes);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel, l.tm_a, l.tm_b, l.p));
 }
 
 void launch_conv_simt(const ConvDesc& d, cudaStream_t s) {

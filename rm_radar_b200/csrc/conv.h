@@ -32,6 +32,9 @@ struct ConvParams {
     const __half* res;
     int res_pitch, res_coff;
     uint32_t idesc, sbo, layout;
+    uint32_t a_bytes, b_bytes, b_off, stage_stride, tmem_cols;   // operand ring geometry
+    int stages, vec_ok;
+    long long* dbg;                   // optional per-CTA clock64 timeline (64 slots per CTA), tests only
 };
 
 struct ConvLaunch {

@@ -139,6 +139,34 @@ void Net::run_steps(const BatchPlan& bp, int batch, cudaStream_t s) {
     }
 }
 
+void Net::run_one(const Step& st, int batch, cudaStream_t s) {
+    BatchPlan one;
+    one.steps.push_back(st);
+    run_steps(one, batch, s);
+}
+
+std::vector<float> Net::profile_ops(int batch, int iters, cudaStream_t s) {
+    if (batch <= 0 || batch > max_batch_ || iters <= 0) throw std::invalid_argument("profile_ops: bad batch / iters");
+    conv_init();
+    BatchPlan& bp = plan_for(batch);
+    std::vector<float> ms(bp.steps.size(), 0.f);
+    cudaEvent_t e0, e1;
+    RMR_CUDA(cudaEventCreate(&e0));
+    RMR_CUDA(cudaEventCreate(&e1));
+    for (size_t i = 0; i < bp.steps.size(); ++i) {
+        run_one(bp.steps[i], batch, s);   // warm
+        RMR_CUDA(cudaEventRecord(e0, s));
+        for (int k = 0; k < iters; ++k) run_one(bp.steps[i], batch, s);
+        RMR_CUDA(cudaEventRecord(e1, s));
+        RMR_CUDA(cudaEventSynchronize(e1));
+        RMR_CUDA(cudaEventElapsedTime(&ms[i], e0, e1));
+        ms[i] /= static_cast<float>(iters);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms;
+}
+
 void Net::forward(int batch, cudaStream_t s) {
     if (batch <= 0) return;
     if (batch > max_batch_) throw std::invalid_argument("batch exceeds max_batch");

@@ -50,6 +50,9 @@ public:
     int max_batch() const { return max_batch_; }
     double flops_per_image() const { return flops_per_image_; }
     int launches_per_forward() const { return static_cast<int>(ops_.size()); }
+    // per-op timing (bench / profiling): ms per launch of every op at `batch`, `iters` back-to-back launches each
+    std::vector<float> profile_ops(int batch, int iters, cudaStream_t s);
+    bool op_uses_umma(int batch, int i) { return plan_for(batch).steps[i].umma; }
     // debugging / tests
     void set_force_simt(bool v) { force_simt_ = v; plans_.clear(); }
     void set_use_graph(bool v) { use_graph_ = v; }
@@ -72,6 +75,7 @@ private:
     };
     BatchPlan& plan_for(int batch);
     void run_steps(const BatchPlan& bp, int batch, cudaStream_t s);
+    void run_one(const Step& st, int batch, cudaStream_t s);
 
     int max_batch_ = 1, in_h_ = 0, in_w_ = 0, num_classes_ = 0, input_buf_ = 0, anchors_ = 0;
     std::vector<EngineBuf> buf_desc_;

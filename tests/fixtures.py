@@ -46,7 +46,12 @@ def onnx(name):
 
 
 def have_models():
-    return all(os.path.exists(os.path.join(ENGINES, n)) for n in ("car.rmeng", "armor.rmeng", "car.onnx", "armor.onnx"))
+    return all(os.path.exists(os.path.join(ENGINES, n)) for n in ("car.rmeng", "armor.rmeng"))
+
+
+def have_onnx():
+    """fp32 ONNX copies for the live torch oracle (114 MB; may be left out of a GPU-box snapshot)."""
+    return all(os.path.exists(os.path.join(ENGINES, n)) for n in ("car.onnx", "armor.onnx"))
 
 
 def load_frame(i):

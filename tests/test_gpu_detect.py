@@ -12,7 +12,8 @@ from tests import fixtures as fx
 
 pytestmark = pytest.mark.gpu
 
-needs_models = pytest.mark.skipif(not fx.have_models(), reason="engines / onnx copies not built")
+needs_models = pytest.mark.skipif(not fx.have_models(), reason="engines not built")
+needs_onnx = pytest.mark.skipif(not fx.have_onnx(), reason="fp32 onnx copies for the live oracle not present")
 
 
 @pytest.fixture(scope="module")
@@ -66,6 +67,7 @@ def test_preprocess_corrected_mode_and_stale_staging():
 
 
 @needs_models
+@needs_onnx
 def test_network_output_vs_fp32_oracle(oracle_nets):
     """Head output [1,5,34000] of the tcgen05 conv stack vs the fp32 ONNX graph on the golden frame.
     fp16 operands / fp32 accumulate: SURVEY C.4 measured 0.009 px / 3e-4; gate at 0.25 px / 4e-3."""
@@ -109,6 +111,7 @@ def test_cascade_golden_frames(robot_detector):
 
 
 @needs_models
+@needs_onnx
 def test_cascade_1080p_matches_live_oracle(robot_detector, oracle_nets):
     """BASELINE config C2 geometry (1920x1080): CUDA path vs the oracle run live on the same frame."""
     exp = np.load(os.path.join(fx.GOLDEN, "expected.npz"))
