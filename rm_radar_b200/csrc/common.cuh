@@ -59,7 +59,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
-        if (spins > (1u << 24)) __trap();
+        if (spins > (1u << 24)) {
+            printf("rmr: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
+            __trap();
+        }
     }
 }
 __device__ __forceinline__ void fence_barrier_init() {

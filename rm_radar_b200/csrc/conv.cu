@@ -27,7 +27,7 @@ namespace rmr {
 namespace {
 
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
 constexpr int kSmemBudget = 100 * 1024;   // operand ring per CTA: two CTAs co-reside on one SM
 
 __device__ __forceinline__ bool elect_one() {
@@ -52,10 +52,13 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-5 = epilogue.
-// Producer and issuer run warp-converged (one elected lane issues) so that the loop bookkeeping
-// stays in the uniform datapath; two CTAs per SM let one CTA's epilogue hide behind the other's
-// main loop.
+// Warp roles: warps 0-3 = activation (A) TMA producers (ring slots round-robin) and, once their loads are
+// out, epilogue; warps 6-9 = epilogue only (two warps per TMEM lane quarter, interleaved column chunks);
+// warp 4 = MMA issuer (+ TMEM owner); warp 5 = weight (B) TMA producer.  A 5-D UTMALDG costs ~200 issue cycles on the issuing thread and a 2-D one ~60
+// (tools/tma_bench2.cu; issue cost is per warp, not a shared unit), while a 128x64x64 MMA block is only
+// 128 tensor cycles: one producer thread cannot feed the tensor core, four can.  Producer and issuer
+// loops run warp-converged (one elected lane issues) so the bookkeeping stays in the uniform datapath;
+// two CTAs per SM let one CTA's epilogue hide behind the other's main loop.
 __global__ void __launch_bounds__(kThreads, 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ ConvParams p) {
@@ -83,13 +86,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
     // ---- setup: nothing here reads activations, so under PDL it overlaps the previous layer ----
-    if (warp == 0) {
+    if (warp == 5) {
         if (lane == 0) {
             tma_prefetch_desc(&tm_a);
             tma_prefetch_desc(&tm_b);
         }
         if (lane < p.ntaps) s_tap[lane] = p.tap[lane];
-    } else if (warp == 1) {
+    } else if (warp == 4) {
         if (lane == 0) {
             for (int i = 0; i < p.stages; ++i) {
                 mbar_init(smem_u32(&bar_full[i]), 1);
@@ -102,8 +105,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
         tmem_relinquish();
     } else {
-        const int t = threadIdx.x - 64;
-        if (t < p.block_n) s_bias[t] = __ldg(p.bias + ch0 + t);
+        if (static_cast<int>(threadIdx.x) < p.block_n) s_bias[threadIdx.x] = __ldg(p.bias + ch0 + threadIdx.x);
     }
     tc_fence_before();
     __syncthreads();
@@ -114,45 +116,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
     const int num_it = p.ntaps * p.kpt;
 
-    if (warp == 0) {
-        // ------------------------------ TMA producer ------------------------------
+    if (warp == 5) {
+        // ------------------------------ B (weight) producer ------------------------------
+        // Weights are constants: no grid dependency, the first ring pass goes out immediately.  A tile's
+        // complete_tx may land before the A producer's expect_tx (the tx-count is signed).
         const bool leader = elect_one();
-        const uint32_t tx = p.a_bytes + p.b_bytes;
-        const int npre = min(p.stages, num_it);
-        // weights are constants: the first ring pass of B tiles goes out before the grid dependency resolves
-        if (leader) {
-            for (int i = 0; i < npre; ++i) {
-                const uint32_t full = smem_u32(&bar_full[i]);
-                mbar_expect_tx(full, tx);
-                tma_load_2d(smem_base + i * p.stage_stride + p.b_off, &tm_b, full, i * p.bk, ch0);
-            }
-        }
-        pdl_wait();
-        int stage = 0, it = 0;
+        int stage = 0;
         uint32_t phase = 0;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-            const int4 t = s_tap[tap];
-            const int cw = ow0 + t.y, chh = oh0 + t.w;
-            int cc = p.cin_coff + t.x;
-            for (int kc = 0; kc < p.kpt; ++kc, ++it, cc += p.bk) {
-                const uint32_t full = smem_u32(&bar_full[stage]);
-                const uint32_t sa = smem_base + stage * p.stage_stride;
-                if (it >= npre) {
-                    mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-                    if (leader) {
-                        mbar_expect_tx(full, tx);
-                        tma_load_2d(sa + p.b_off, &tm_b, full, it * p.bk, ch0);
-                    }
-                }
-                if (leader) {
-                    if (dbg && it < 16) dbg[24 + it] = clock64();
-                    tma_load_5d(sa, &tm_a, full, cc, cw, t.z, chh, n0);
-                }
-                __syncwarp();
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-            }
+        for (int it = 0; it < num_it; ++it) {
+            if (it >= p.stages) mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+            if (leader)
+                tma_load_2d(smem_base + stage * p.stage_stride + p.b_off, &tm_b, smem_u32(&bar_full[stage]),
+                            it * p.bk, ch0);
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-    } else if (warp == 1) {
+    } else if (warp == 4) {
         // ------------------------------ MMA issuer ------------------------------
         const bool leader = elect_one();
         const uint64_t adesc0 = umma_smem_desc(smem_base, p.sbo, p.layout);
@@ -182,8 +161,38 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         __syncwarp();
     } else {
-        // ---------------- epilogue: 4 warps, one TMEM lane quarter each ----------------
+        // ---------------- warps 0-3: A (activation) producers ----------------
+        // Ring slot s belongs to warp s % 4 for the whole kernel: a slot's owner meets its empty barrier
+        // round after round, so it is never more than one phase ahead of it (a parity wait cannot tell
+        // phases two apart).
+        pdl_wait();   // activations, residual reads and output writes must follow the previous grid
+        if (warp < 4) {
+            const bool leader = elect_one();
+            const uint32_t tx = p.a_bytes + p.b_bytes;
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+                const int4 t = s_tap[tap];
+                for (int kc = 0; kc < p.kpt; ++kc, ++it) {
+                    if ((stage & 3) == warp) {
+                        const uint32_t full = smem_u32(&bar_full[stage]);
+                        if (it >= p.stages) mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                        if (leader) {
+                            mbar_expect_tx(full, tx);
+                            if (dbg && it < 16) dbg[24 + it] = clock64();
+                            tma_load_5d(smem_base + stage * p.stage_stride, &tm_a, full,
+                                        p.cin_coff + t.x + kc * p.bk, ow0 + t.y, t.z, oh0 + t.w, n0);
+                        }
+                        __syncwarp();
+                    }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        // ---------------- epilogue: warps 0-3 and 6-9; TMEM lane quarter = warp % 4 ----------------
+        // the two warps of a quarter interleave 32-column chunks (0, 64, .. / 32, 96, ..)
         const int q = warp & 3;
+        const int chunk0 = warp >= 6 ? 32 : 0;
         const int row = q * 32 + lane;
         const int tw_i = row % p.tw;
         const int th_i = (row / p.tw) % p.th;
@@ -195,7 +204,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const __half* rptr = (p.res != nullptr && valid) ? p.res + pix * p.res_pitch + p.res_coff + ch0 : nullptr;
         const bool vec = p.vec_ok != 0;
 
-        pdl_wait();   // residual reads and output writes must follow the previous grid
         uint4 rnext[4];
         auto fetch_res = [&](int c0) {
             const int cnt = nvalid - c0;
@@ -208,22 +216,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
             }
         };
-        fetch_res(0);
+        fetch_res(chunk0);
 
         mbar_wait(smem_u32(&bar_acc), 0);
-        if (dbg && threadIdx.x == 64) dbg[19] = clock64();
+        if (dbg && threadIdx.x == 0) dbg[19] = clock64();
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        for (int c0 = 0; c0 < nvalid; c0 += 32) {
+        for (int c0 = chunk0; c0 < nvalid; c0 += 64) {
             uint32_t v[32];
             __syncwarp();   // tcgen05.ld is warp-aligned: reconverge after the predicated stores
             tmem_ld_32(taddr + c0, v);
             uint4 rcur[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-            if (c0 + 32 < nvalid) fetch_res(c0 + 32);
+            if (c0 + 64 < nvalid) fetch_res(c0 + 64);
             tmem_ld_wait();
-            if (dbg && threadIdx.x == 64 && c0 == 0) dbg[40] = clock64();
+            if (dbg && threadIdx.x == 0 && c0 == chunk0) dbg[40] = clock64();
             if (valid) {
             const int cnt = min(32, nvalid - c0);
             float f[32];
@@ -262,7 +270,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         if (j < cnt) f[j] += __half2float(rptr[c0 + j]);
                 }
             }
-            if (dbg && threadIdx.x == 64 && c0 == 0) dbg[41] = clock64() + (__float_as_int(f[0]) & 0);
+            if (dbg && threadIdx.x == 0 && c0 == chunk0) dbg[41] = clock64() + (__float_as_int(f[0]) & 0);
             if (p.out_f32) {
                 float* o = static_cast<float*>(p.out) + pix * p.out_pitch + p.out_coff + ch0 + c0;
                 if (vec && (cnt & 3) == 0) {
@@ -295,16 +303,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
             }
             }
-            if (dbg && threadIdx.x == 64 && c0 == 0) dbg[42] = clock64();
+            if (dbg && threadIdx.x == 0 && c0 == chunk0) dbg[42] = clock64();
         }
         __syncwarp();
-        if (dbg && threadIdx.x == 64) dbg[20] = clock64();
+        if (dbg && threadIdx.x == 0) dbg[20] = clock64();
     }
 
     tc_fence_before();
     __syncthreads();
     if (dbg && threadIdx.x == 0) dbg[21] = clock64();
-    if (warp == 1) {
+    if (warp == 4) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
@@ -616,7 +624,7 @@ void conv_init() {
     });
 }
 
-void launch_conv_umma(const ConvLaunch& l, cudaStream_t s) {
+void launch_conv_umma(const ConvLaunch& l, cudaStream_t s, bool pdl) {
     conv_init();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = l.grid;
@@ -627,7 +635,7 @@ void launch_conv_umma(const ConvLaunch& l, cudaStream_t s) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    cfg.numAttrs = (g_use_pdl && pdl) ? 1 : 0;
     RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel, l.tm_a, l.tm_b, l.p));
 }
 

@@ -48,7 +48,7 @@ struct ConvLaunch {
 void conv_init();   // one-time function attributes; must run outside stream capture
 bool conv_umma_supported(const ConvDesc& d);
 ConvLaunch make_conv_launch(const ConvDesc& d);
-void launch_conv_umma(const ConvLaunch& l, cudaStream_t s);
+void launch_conv_umma(const ConvLaunch& l, cudaStream_t s, bool pdl = true);
 // generic direct convolution on CUDA cores: the stem (Cin=3) and the on-device checker for tests
 void launch_conv_simt(const ConvDesc& d, cudaStream_t s);
 

@@ -150,21 +150,38 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(const int* __restrict
     }
 }
 
-// Row-major stable compaction of foreground pixels + back-projection (locate.cpp:237-250): the point
-// index equals the reference's cloud_foreground_ index.  Also initialises union-find + cell hash.
-__device__ __forceinline__ unsigned cell_hash(int ix, int iy, int iz, unsigned mask) {
-    unsigned h = static_cast<unsigned>(ix) * 73856093u ^ static_cast<unsigned>(iy) * 19349663u ^
-                 static_cast<unsigned>(iz) * 83492791u;
-    h ^= h >> 15;
-    return h & mask;
+// ---- radius graph on a fine cell grid ----
+// Cell edge = kCellFrac * tolerance with kCellFrac < 1/sqrt(3): any two points of one cell are closer
+// than the tolerance (diagonal = 0.987 tol, a margin far above float rounding), so a whole cell is one
+// union without a single distance test, and a point has neighbours only in the 5x5x5 cells around it.
+constexpr float kCellFrac = 0.57f;
+constexpr unsigned long long kEmptyKey = ~0ull;
+
+__device__ __forceinline__ unsigned long long cell_key(int ix, int iy, int iz) {
+    return (static_cast<unsigned long long>(static_cast<unsigned>(ix + (1 << 20)) & 0x1FFFFFu) << 42) |
+           (static_cast<unsigned long long>(static_cast<unsigned>(iy + (1 << 20)) & 0x1FFFFFu) << 21) |
+           static_cast<unsigned long long>(static_cast<unsigned>(iz + (1 << 20)) & 0x1FFFFFu);
+}
+__device__ __forceinline__ unsigned key_hash(unsigned long long k, unsigned mask) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33;
+    return static_cast<unsigned>(k) & mask;
+}
+__device__ __forceinline__ int3 cell_of(const LocateCalib& c, float x, float y, float z) {
+    const float inv = 1.f / (kCellFrac * c.tol);
+    return make_int3(static_cast<int>(floorf(x * inv)), static_cast<int>(floorf(y * inv)),
+                     static_cast<int>(floorf(z * inv)));
 }
 
+// Row-major stable compaction of foreground pixels + back-projection (locate.cpp:237-250): the point
+// index equals the reference's cloud_foreground_ index.  Also initialises union-find and threads the
+// point onto its cell's list (exact cell match: open addressing on the packed cell coordinates).
 __global__ void __launch_bounds__(256) compact_kernel(const __grid_constant__ LocateCalib c, int npix,
                                                       const float* __restrict__ diff,
                                                       const int* __restrict__ block_offsets, int max_fg,
                                                       float* __restrict__ fg_pts, int* __restrict__ parent,
                                                       int* __restrict__ next, int* __restrict__ heads,
-                                                      unsigned hash_mask, int* __restrict__ comp_size) {
+                                                      unsigned long long* __restrict__ keys, unsigned hash_mask,
+                                                      int* __restrict__ comp_size) {
     __shared__ int warp_tot[8];
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     const float depth = pix < npix ? diff[pix] : 0.f;
@@ -182,9 +199,14 @@ __global__ void __launch_bounds__(256) compact_kernel(const __grid_constant__ Lo
     reinterpret_cast<float4*>(fg_pts)[idx] = make_float4(p.x, p.y, p.z, __int_as_float(pix));
     parent[idx] = idx;
     comp_size[idx] = 0;
-    const float inv = 1.f / c.tol;
-    const unsigned h = cell_hash(static_cast<int>(floorf(p.x * inv)), static_cast<int>(floorf(p.y * inv)),
-                                 static_cast<int>(floorf(p.z * inv)), hash_mask);
+    const int3 ci = cell_of(c, p.x, p.y, p.z);
+    const unsigned long long key = cell_key(ci.x, ci.y, ci.z);
+    unsigned h = key_hash(key, hash_mask);
+    while (true) {
+        const unsigned long long prev = atomicCAS(keys + h, kEmptyKey, key);
+        if (prev == kEmptyKey || prev == key) break;
+        h = (h + 1) & hash_mask;
+    }
     next[idx] = atomicExch(heads + h, idx);
 }
 
@@ -216,40 +238,57 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
     }
 }
 
-// Radius graph by cell hashing (cell edge = tolerance): a neighbour within the tolerance lies in
-// one of the 27 surrounding cells.  Buckets may mix cells (hash collisions) — harmless, the true
-// squared distance decides.  Roots are minimal member indices, so the partition is deterministic.
-__global__ void __launch_bounds__(128) link_kernel(const __grid_constant__ LocateCalib c,
+// One thread per (point, neighbour cell).  Slot 0 chains the point to the next one on its own cell's
+// list (same cell => within tolerance).  Slots 1..62 cover the half space of the 124 surrounding
+// cells, so that each unordered pair of cells is examined from exactly one side: the thread walks the
+// neighbour cell's list up to the first point within the tolerance and unions with it — the rest of
+// that cell is already one component.  Every union is backed by a genuine edge of the radius graph and
+// every edge ends up inside one component, so the partition equals the exact connected components
+// (PCL EuclideanClusterExtraction, locate.cpp:255-257); roots are minimal member indices.
+constexpr int kLinkSlots = 63;
+__global__ void __launch_bounds__(256) link_kernel(const __grid_constant__ LocateCalib c,
                                                    const int* __restrict__ counters,
                                                    const float* __restrict__ fg_pts, int* __restrict__ parent,
                                                    const int* __restrict__ next, const int* __restrict__ heads,
-                                                   unsigned hash_mask) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                                   const unsigned long long* __restrict__ keys, unsigned hash_mask) {
     const int n = counters[0];
-    if (i >= n) return;
-    const float4 p = reinterpret_cast<const float4*>(fg_pts)[i];
-    const float inv = 1.f / c.tol;
-    const int cx = static_cast<int>(floorf(p.x * inv)), cy = static_cast<int>(floorf(p.y * inv)),
-              cz = static_cast<int>(floorf(p.z * inv));
+    const long total = static_cast<long>(n) * kLinkSlots;
     const float tol2 = __fmul_rn(c.tol, c.tol);
-    unsigned seen[27];
-    int nseen = 0;
-    for (int dz = -1; dz <= 1; ++dz)
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-                const unsigned h = cell_hash(cx + dx, cy + dy, cz + dz, hash_mask);
-                bool dup = false;
-                for (int k = 0; k < nseen; ++k) dup |= (seen[k] == h);
-                if (dup) continue;
-                seen[nseen++] = h;
-                for (int j = heads[h]; j >= 0; j = next[j]) {
-                    if (j >= i) continue;   // each unordered pair once
-                    const float4 q = reinterpret_cast<const float4*>(fg_pts)[j];
-                    const float ex = __fsub_rn(p.x, q.x), ey = __fsub_rn(p.y, q.y), ez = __fsub_rn(p.z, q.z);
-                    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
-                    if (d2 < tol2) uf_union(parent, i, j);
-                }
+    // grid-stride: the grid is sized for the machine, not for max_foreground
+    for (long t = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+         t += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int i = static_cast<int>(t / kLinkSlots);
+        const int slot = static_cast<int>(t - static_cast<long>(i) * kLinkSlots);
+        if (slot == 0) {
+            const int j = next[i];
+            if (j >= 0) uf_union(parent, i, j);
+            continue;
+        }
+        // half-space enumeration of (dx, dy, dz) in [-2, 2]^3 \ {0}: slot s -> linear index 62 + s
+        const int lin = 62 + slot;
+        const int dz = lin / 25 - 2, dy = (lin / 5) % 5 - 2, dx = lin % 5 - 2;
+        const float4 p = reinterpret_cast<const float4*>(fg_pts)[i];
+        const int3 ci = cell_of(c, p.x, p.y, p.z);
+        const unsigned long long key = cell_key(ci.x + dx, ci.y + dy, ci.z + dz);
+        unsigned h = key_hash(key, hash_mask);
+        bool found = false;
+        while (true) {
+            const unsigned long long k = keys[h];
+            if (k == key) { found = true; break; }
+            if (k == kEmptyKey) break;
+            h = (h + 1) & hash_mask;
+        }
+        if (!found) continue;
+        for (int j = heads[h]; j >= 0; j = next[j]) {
+            const float4 q = reinterpret_cast<const float4*>(fg_pts)[j];
+            const float ex = __fsub_rn(p.x, q.x), ey = __fsub_rn(p.y, q.y), ez = __fsub_rn(p.z, q.z);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+            if (d2 < tol2) {
+                uf_union(parent, i, j);
+                break;
             }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) flatten_kernel(const int* __restrict__ counters, int* __restrict__ parent,
@@ -488,6 +527,7 @@ Locator::Locator(const LocatorConfig& cfg, int max_points, int max_foreground, i
     RMR_CUDA(cudaMalloc(&parent_, sizeof(int) * max_fg_));
     RMR_CUDA(cudaMalloc(&next_, sizeof(int) * max_fg_));
     RMR_CUDA(cudaMalloc(&heads_, sizeof(int) * hash_size_));
+    RMR_CUDA(cudaMalloc(&cell_keys_, sizeof(unsigned long long) * hash_size_));
     RMR_CUDA(cudaMalloc(&comp_size_, sizeof(int) * max_fg_));
     RMR_CUDA(cudaMalloc(&cluster_id_, sizeof(int) * max_fg_));
     RMR_CUDA(cudaMalloc(&root_list_, sizeof(int) * (kMaxClusters + 1)));
@@ -502,7 +542,7 @@ Locator::Locator(const LocatorConfig& cfg, int max_points, int max_foreground, i
 Locator::~Locator() {
     cudaFree(cloud_); cudaFreeHost(pinned_cloud_); cudaFree(packed_); cudaFree(bg_); cudaFree(diff_);
     cudaFree(ring_); cudaFree(label_img_); cudaFree(block_counts_); cudaFree(block_offsets_); cudaFree(counters_);
-    cudaFree(fg_pts_); cudaFree(parent_); cudaFree(next_); cudaFree(heads_); cudaFree(comp_size_);
+    cudaFree(fg_pts_); cudaFree(parent_); cudaFree(next_); cudaFree(heads_); cudaFree(cell_keys_); cudaFree(comp_size_);
     cudaFree(cluster_id_); cudaFree(root_list_); cudaFree(hist_); cudaFree(dev_rects_); cudaFree(dev_results_);
     cudaFreeHost(pinned_rects_); cudaFreeHost(pinned_results_);
 }
@@ -564,11 +604,12 @@ void Locator::update_device(const float* dev_points, int n, int stride_floats, c
 void Locator::cluster(cudaStream_t s) {
     scan_blocks_kernel<<<1, 1024, 0, s>>>(block_counts_, block_offsets_, nblocks_, counters_, max_fg_);
     RMR_CUDA(cudaMemsetAsync(heads_, 0xFF, sizeof(int) * hash_size_, s));
+    RMR_CUDA(cudaMemsetAsync(cell_keys_, 0xFF, sizeof(unsigned long long) * hash_size_, s));
     compact_kernel<<<nblocks_, 256, 0, s>>>(calib_, npix_, diff_, block_offsets_, max_fg_, fg_pts_, parent_, next_,
-                                            heads_, static_cast<unsigned>(hash_size_ - 1), comp_size_);
-    const int fg_blocks128 = (max_fg_ + 127) / 128, fg_blocks256 = (max_fg_ + 255) / 256;
-    link_kernel<<<fg_blocks128, 128, 0, s>>>(calib_, counters_, fg_pts_, parent_, next_, heads_,
-                                             static_cast<unsigned>(hash_size_ - 1));
+                                            heads_, cell_keys_, static_cast<unsigned>(hash_size_ - 1), comp_size_);
+    const int fg_blocks256 = (max_fg_ + 255) / 256;
+    link_kernel<<<148 * 8, 256, 0, s>>>(
+        calib_, counters_, fg_pts_, parent_, next_, heads_, cell_keys_, static_cast<unsigned>(hash_size_ - 1));
     flatten_kernel<<<fg_blocks256, 256, 0, s>>>(counters_, parent_, comp_size_);
     collect_roots_kernel<<<fg_blocks256, 256, 0, s>>>(calib_, counters_, parent_, comp_size_, root_list_);
     rank_roots_kernel<<<(kMaxClusters + 255) / 256, 256, 0, s>>>(counters_, comp_size_, root_list_, cluster_id_);

@@ -83,6 +83,7 @@ private:
     int *block_counts_ = nullptr, *block_offsets_ = nullptr;
     int* counters_ = nullptr;              // [0]=fg count, [1]=num clusters, [2]=valid-root count
     float* fg_pts_ = nullptr;              // [max_fg][4]: x,y,z,pixel index bits
+    unsigned long long* cell_keys_ = nullptr;   // open-addressing hash: packed (ix, iy, iz) of occupied cells
     int *parent_ = nullptr, *next_ = nullptr, *heads_ = nullptr, *comp_size_ = nullptr, *cluster_id_ = nullptr,
         *root_list_ = nullptr;
     int* hist_ = nullptr;                  // [max_robots][kMaxClusters + 1]

@@ -1,5 +1,6 @@
 #include "net.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -68,6 +69,8 @@ Net::Net(const std::string& engine_path, int max_batch) : max_batch_(max_batch) 
     force_simt_ = e && e[0] == '1';
     const char* g = std::getenv("RMR_NO_GRAPH");
     use_graph_ = !(g && g[0] == '1');
+    const char* ln = std::getenv("RMR_GRAPH_LANES");
+    if (ln) max_lanes_ = std::max(1, std::min(16, std::atoi(ln)));
 }
 
 Net::~Net() {
@@ -107,36 +110,159 @@ Net::BatchPlan& Net::plan_for(int batch) {
         }
         bp.steps.push_back(st);
     }
+    schedule(bp);
     return plans_.emplace(batch, std::move(bp)).first->second;
 }
 
-void Net::run_steps(const BatchPlan& bp, int batch, cudaStream_t s) {
-    for (const Step& st : bp.steps) {
-        const EngineOp& op = st.op;
-        switch (st.type) {
-            case OP_CONV:
-                if (st.umma) launch_conv_umma(st.launch, s);
-                else launch_conv_simt(st.desc, s);
-                break;
-            case OP_MAXPOOL5:
-                launch_maxpool5(static_cast<const __half*>(bufs_[op.src_buf]), buf_desc_[op.src_buf].c, op.src_coff,
-                                static_cast<__half*>(bufs_[op.dst_buf]), buf_desc_[op.dst_buf].c, op.dst_coff, batch,
-                                op.src_h, op.src_w, op.src_c, s);
-                break;
-            case OP_UPSAMPLE2:
-                launch_upsample2(static_cast<const __half*>(bufs_[op.src_buf]), buf_desc_[op.src_buf].c, op.src_coff,
-                                 static_cast<__half*>(bufs_[op.dst_buf]), buf_desc_[op.dst_buf].c, op.dst_coff, batch,
-                                 op.src_h, op.src_w, op.src_c, s);
-                break;
-            case OP_COPY:
-                launch_copy_channels(static_cast<const __half*>(bufs_[op.src_buf]), buf_desc_[op.src_buf].c,
-                                     op.src_coff, static_cast<__half*>(bufs_[op.dst_buf]), buf_desc_[op.dst_buf].c,
-                                     op.dst_coff, batch, op.src_h, op.src_w, op.src_c, s);
-                break;
-            default:
-                throw std::runtime_error("unknown engine op");
-        }
+void Net::launch_step(const Step& st, int batch, cudaStream_t s, bool pdl) {
+    const EngineOp& op = st.op;
+    switch (st.type) {
+        case OP_CONV:
+            if (st.umma) launch_conv_umma(st.launch, s, pdl);
+            else launch_conv_simt(st.desc, s);
+            break;
+        case OP_MAXPOOL5:
+            launch_maxpool5(static_cast<const __half*>(bufs_[op.src_buf]), buf_desc_[op.src_buf].c, op.src_coff,
+                            static_cast<__half*>(bufs_[op.dst_buf]), buf_desc_[op.dst_buf].c, op.dst_coff, batch,
+                            op.src_h, op.src_w, op.src_c, s);
+            break;
+        case OP_UPSAMPLE2:
+            launch_upsample2(static_cast<const __half*>(bufs_[op.src_buf]), buf_desc_[op.src_buf].c, op.src_coff,
+                             static_cast<__half*>(bufs_[op.dst_buf]), buf_desc_[op.dst_buf].c, op.dst_coff, batch,
+                             op.src_h, op.src_w, op.src_c, s);
+            break;
+        case OP_COPY:
+            launch_copy_channels(static_cast<const __half*>(bufs_[op.src_buf]), buf_desc_[op.src_buf].c,
+                                 op.src_coff, static_cast<__half*>(bufs_[op.dst_buf]), buf_desc_[op.dst_buf].c,
+                                 op.dst_coff, batch, op.src_h, op.src_w, op.src_c, s);
+            break;
+        default:
+            throw std::runtime_error("unknown engine op");
     }
+}
+
+void Net::run_steps(const BatchPlan& bp, int batch, cudaStream_t s) {
+    for (const Step& st : bp.steps) launch_step(st, batch, s, true);
+}
+
+// Dependency analysis over buffer views (buffer, channel range): RAW, WAR and WAW hazards give the
+// partial order; ops are then laid out on up to max_lanes_ capture streams so that independent
+// branches (the 2 x 4 head branches, head levels vs. the rest of the neck) become parallel graph
+// branches.  An op continues the lane of its most recent producer when that producer is still the
+// lane's tail; otherwise it opens / reuses another lane.
+void Net::schedule(BatchPlan& bp) {
+    struct View { int buf, c0, c1; };
+    const int n = static_cast<int>(bp.steps.size());
+    auto overlap = [](const View& a, const View& b) { return a.buf == b.buf && a.c0 < b.c1 && b.c0 < a.c1; };
+    std::vector<std::vector<View>> reads(n), writes(n);
+    for (int i = 0; i < n; ++i) {
+        const EngineOp& op = bp.steps[i].op;
+        reads[i].push_back(View{op.src_buf, op.src_coff, op.src_coff + op.src_c});
+        if (op.type == OP_CONV && op.res_buf >= 0) reads[i].push_back(View{op.res_buf, op.res_coff, op.res_coff + op.dst_c});
+        const int wc = (op.type == OP_CONV) ? op.dst_c : op.src_c;
+        writes[i].push_back(View{op.dst_buf, op.dst_coff, op.dst_coff + wc});
+    }
+    std::vector<std::vector<int>> preds(n);
+    for (int i = 0; i < n; ++i)
+        for (int j = i - 1; j >= 0; --j) {
+            bool dep = false;
+            for (const View& w : writes[j]) {
+                for (const View& r : reads[i]) dep |= overlap(w, r);    // RAW
+                for (const View& w2 : writes[i]) dep |= overlap(w, w2); // WAW
+            }
+            for (const View& r : reads[j])
+                for (const View& w2 : writes[i]) dep |= overlap(r, w2); // WAR
+            if (dep) preds[i].push_back(j);
+        }
+    std::vector<int> tail(max_lanes_, -1);      // last op recorded on each lane
+    int lanes_used = 1;
+    for (int i = 0; i < n; ++i) {
+        Step& st = bp.steps[i];
+        int lane = -1;
+        for (int j : preds[i])                   // preds are in descending order: most recent producer first
+            if (tail[bp.steps[j].lane] == j) { lane = bp.steps[j].lane; break; }
+        if (lane < 0) {
+            if (i == 0) lane = 0;
+            else if (lanes_used < max_lanes_) lane = lanes_used++;
+            else {
+                // all lanes busy: queue behind the lane whose tail is oldest
+                lane = 0;
+                for (int l = 1; l < max_lanes_; ++l)
+                    if (tail[l] < tail[lane]) lane = l;
+            }
+        }
+        st.lane = lane;
+        st.deps.clear();
+        for (int j : preds[i])
+            if (bp.steps[j].lane != lane) {
+                st.deps.push_back(j);
+                bp.steps[j].signals = true;
+            }
+        tail[lane] = i;
+    }
+    bp.lanes = lanes_used;
+}
+
+// Stream capture of the scheduled plan: lane 0 is the origin stream, other lanes fork from it through
+// event waits and are joined back before EndCapture.  Consecutive tcgen05 convs on one lane keep their
+// programmatic (PDL) edge; an op that also waits on another lane is launched with a full dependency.
+void Net::capture(BatchPlan& bp, int batch) {
+    conv_init();
+    const int n = static_cast<int>(bp.steps.size());
+    std::vector<cudaStream_t> ls(bp.lanes, nullptr);
+    std::vector<cudaEvent_t> ev(n, nullptr);
+    std::vector<cudaEvent_t> extra;
+    cudaGraph_t g = nullptr;
+    auto cleanup = [&] {
+        for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : extra) cudaEventDestroy(e);
+        for (cudaStream_t s : ls) if (s) cudaStreamDestroy(s);
+    };
+    try {
+        for (auto& s : ls) RMR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        RMR_CUDA(cudaStreamBeginCapture(ls[0], cudaStreamCaptureModeThreadLocal));
+        cudaEvent_t fork;
+        RMR_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        extra.push_back(fork);
+        RMR_CUDA(cudaEventRecord(fork, ls[0]));
+        std::vector<bool> joined(bp.lanes, false);
+        joined[0] = true;
+        for (int i = 0; i < n; ++i) {
+            const Step& st = bp.steps[i];
+            cudaStream_t s = ls[st.lane];
+            if (!joined[st.lane]) {
+                RMR_CUDA(cudaStreamWaitEvent(s, fork, 0));
+                joined[st.lane] = true;
+            }
+            for (int j : st.deps) RMR_CUDA(cudaStreamWaitEvent(s, ev[j], 0));
+            launch_step(st, batch, s, st.deps.empty());
+            if (st.signals) {
+                RMR_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+                RMR_CUDA(cudaEventRecord(ev[i], s));
+            }
+        }
+        for (int l = 1; l < bp.lanes; ++l) {
+            if (!joined[l]) continue;
+            cudaEvent_t e;
+            RMR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            extra.push_back(e);
+            RMR_CUDA(cudaEventRecord(e, ls[l]));
+            RMR_CUDA(cudaStreamWaitEvent(ls[0], e, 0));
+        }
+        RMR_CUDA(cudaStreamEndCapture(ls[0], &g));
+        RMR_CUDA(cudaGraphInstantiate(&bp.graph, g, 0));
+    } catch (...) {
+        cudaGraph_t dead = nullptr;
+        cudaStreamCaptureStatus cst;
+        if (ls[0] && cudaStreamIsCapturing(ls[0], &cst) == cudaSuccess && cst != cudaStreamCaptureStatusNone)
+            cudaStreamEndCapture(ls[0], &dead);
+        if (dead) cudaGraphDestroy(dead);
+        if (g) cudaGraphDestroy(g);
+        cleanup();
+        throw;
+    }
+    cudaGraphDestroy(g);
+    cleanup();
 }
 
 void Net::run_one(const Step& st, int batch, cudaStream_t s) {
@@ -175,32 +301,7 @@ void Net::forward(int batch, cudaStream_t s) {
         run_steps(bp, batch, s);
         return;
     }
-    if (bp.graph == nullptr) {
-        conv_init();
-        // capture on a private stream: the caller's stream may be the legacy default stream, which
-        // cannot be captured, and nothing executes during capture anyway
-        cudaStream_t cs = nullptr;
-        RMR_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-        cudaGraph_t g = nullptr;
-        cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
-        if (e != cudaSuccess) {
-            cudaStreamDestroy(cs);
-            RMR_CUDA(e);
-        }
-        try {
-            run_steps(bp, batch, cs);
-        } catch (...) {
-            cudaStreamEndCapture(cs, &g);
-            if (g) cudaGraphDestroy(g);
-            cudaStreamDestroy(cs);
-            throw;
-        }
-        e = cudaStreamEndCapture(cs, &g);
-        cudaStreamDestroy(cs);
-        RMR_CUDA(e);
-        RMR_CUDA(cudaGraphInstantiate(&bp.graph, g, 0));
-        cudaGraphDestroy(g);
-    }
+    if (bp.graph == nullptr) capture(bp, batch);
     RMR_CUDA(cudaGraphLaunch(bp.graph, s));
 }
 

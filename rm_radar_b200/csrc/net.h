@@ -68,14 +68,21 @@ private:
         ConvDesc desc;
         ConvLaunch launch;
         EngineOp op;
+        int lane = 0;               // capture stream this op is recorded on (independent branches overlap)
+        std::vector<int> deps;      // ops on other lanes that must finish first (RAW / WAR / WAW on buffer views)
+        bool signals = false;       // some op on another lane depends on this one
     };
     struct BatchPlan {
         std::vector<Step> steps;
         cudaGraphExec_t graph = nullptr;
+        int lanes = 1;
     };
     BatchPlan& plan_for(int batch);
     void run_steps(const BatchPlan& bp, int batch, cudaStream_t s);
     void run_one(const Step& st, int batch, cudaStream_t s);
+    void launch_step(const Step& st, int batch, cudaStream_t s, bool pdl);
+    void schedule(BatchPlan& bp);
+    void capture(BatchPlan& bp, int batch);
 
     int max_batch_ = 1, in_h_ = 0, in_w_ = 0, num_classes_ = 0, input_buf_ = 0, anchors_ = 0;
     std::vector<EngineBuf> buf_desc_;
@@ -86,6 +93,7 @@ private:
     std::map<int, BatchPlan> plans_;
     bool force_simt_ = false;
     bool use_graph_ = true;
+    int max_lanes_ = 8;
     double flops_per_image_ = 0;
 };
 
