@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception as e:   # noqa: BLE001
             log("clock sampler unavailable:", e)
@@ -87,6 +87,19 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed `ncu --set full` summary
+    (profiles/*_conv_full.json, written by tools_ncu_summary.py); None when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_conv_full.json")))
+    if not files:
+        return None
+    try:
+        return json.load(open(files[-1])).get("dram_bytes_per_launch_mean")
+    except Exception:   # noqa: BLE001
+        return None
 
 
 def peaks():
@@ -162,6 +175,7 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     import rm_radar_b200 as rr
     from rm_radar_b200 import _lib
+    from rm_radar_b200 import dist as rdist
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -189,17 +203,12 @@ def run_ours(args, rank, world, local_rank):
     lib = _lib.load()
 
     def publish(recs, n):
-        """world-frame robot positions of this rank -> fixed-size block -> NCCL all-gather (N>1)."""
+        """world-frame robot positions of this rank -> fixed-size block -> one NCCL all-gather (N>1)."""
         if world == 1:
             return
-        pos_pin.zero_()
-        for i in range(n):
-            r = recs[i]
-            pos_pin[i, 0] = 1.0; pos_pin[i, 1] = r.label; pos_pin[i, 2] = r.confidence
-            pos_pin[i, 3] = r.is_located
-            pos_pin[i, 4] = r.location[0]; pos_pin[i, 5] = r.location[1]; pos_pin[i, 6] = r.location[2]
+        rdist.pack_records(recs, n, fx.MAX_BATCH, out=pos_pin)
         gather_in.copy_(pos_pin, non_blocking=True)
-        dist.all_gather_into_tensor(gather_out, gather_in)
+        rdist.all_gather_records(gather_in, gather_out)
 
     def step_resident(i):
         j = i % POOL
@@ -272,7 +281,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int((stats["kernel_launches"] + locate_launches) * args.steps),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved_tf / peak_tf, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "kernel": "conv_umma_kernel (tcgen05 implicit GEMM), all conv launches of one frame",
                      "flops_per_step": stats["conv_flops"], "conv_ms_per_step": conv_ms,
                      "car_net_ms": car_ms, "armor_net_ms": armor_ms, "armor_batch": k_cars,

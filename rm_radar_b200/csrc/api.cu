@@ -395,6 +395,12 @@ int rmr_conv_selftest(int n, int h_in, int w_in, int cin, int cout, int k, int s
         RMR_CUDA(cudaStreamCreate(&s));
         d.out = d_out_a;
         ConvLaunch l = make_conv_launch(d);
+        void* d_scratch = nullptr;
+        if (conv_scratch_bytes(l)) {
+            RMR_CUDA(cudaMalloc(&d_scratch, conv_scratch_bytes(l)));
+            RMR_CUDA(cudaMemset(d_scratch, 0, conv_scratch_bytes(l)));
+            conv_bind_scratch(l, d_scratch);
+        }
         launch_conv_umma(l, s);
         ConvDesc dr = d;
         dr.out = d_out_b;
@@ -431,6 +437,7 @@ int rmr_conv_selftest(int n, int h_in, int w_in, int cin, int cout, int k, int s
         }
         cudaStreamDestroy(s);
         cudaFree(d_in); cudaFree(d_w); cudaFree(d_res); cudaFree(d_bias); cudaFree(d_out_a); cudaFree(d_out_b);
+        cudaFree(d_scratch);
     });
 }
 
@@ -458,7 +465,13 @@ int rmr_conv_timeline(int n, int h_in, int w_in, int cin, int cout, int k, int s
         d.h_out = h_out; d.w_out = w_out; d.k = k; d.stride = stride; d.act = 1;
         d.w = d_w; d.bias = d_bias; d.cout_pad = cout_pad; d.cin_pad = cin; d.n = n;
         ConvLaunch l = make_conv_launch(d);
-        const int ctas = static_cast<int>(l.grid.x * l.grid.y);
+        void* d_scratch = nullptr;
+        if (conv_scratch_bytes(l)) {
+            RMR_CUDA(cudaMalloc(&d_scratch, conv_scratch_bytes(l)));
+            RMR_CUDA(cudaMemset(d_scratch, 0, conv_scratch_bytes(l)));
+            conv_bind_scratch(l, d_scratch);
+        }
+        const int ctas = static_cast<int>(l.grid.x * l.grid.y * l.grid.z);
         long long* d_dbg;
         RMR_CUDA(cudaMalloc(&d_dbg, sizeof(long long) * 64 * ctas));
         RMR_CUDA(cudaMemset(d_dbg, 0, sizeof(long long) * 64 * ctas));
@@ -471,7 +484,7 @@ int rmr_conv_timeline(int n, int h_in, int w_in, int cin, int cout, int k, int s
         *n_ctas = ctas;
         RMR_CUDA(cudaMemcpy(out, d_dbg, sizeof(long long) * 64 * std::min(ctas, capacity_ctas), cudaMemcpyDeviceToHost));
         cudaStreamDestroy(s);
-        cudaFree(d_in); cudaFree(d_w); cudaFree(d_out); cudaFree(d_bias); cudaFree(d_dbg);
+        cudaFree(d_in); cudaFree(d_w); cudaFree(d_out); cudaFree(d_bias); cudaFree(d_dbg); cudaFree(d_scratch);
     });
 }
 

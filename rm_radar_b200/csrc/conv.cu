@@ -59,6 +59,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // 128 tensor cycles: one producer thread cannot feed the tensor core, four can.  Producer and issuer
 // loops run warp-converged (one elected lane issues) so the bookkeeping stays in the uniform datapath;
 // two CTAs per SM let one CTA's epilogue hide behind the other's main loop.
+template <bool kSplit>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ ConvParams p) {
@@ -69,6 +70,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     __shared__ uint32_t tmem_base_slot;
     __shared__ int4 s_tap[9];
     __shared__ float s_bias[128];
+    __shared__ int s_last;
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5;
@@ -82,7 +84,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int tile_n = mt / p.tiles_h;
     const int ow0 = tile_w * p.tw, oh0 = tile_h * p.th, n0 = tile_n * p.tn;
     const int ch0 = blockIdx.y * p.block_n;   // first output channel of this CTA
-    long long* dbg = p.dbg ? p.dbg + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
+    long long* dbg = p.dbg ? p.dbg + ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
     // ---- setup: nothing here reads activations, so under PDL it overlaps the previous layer ----
@@ -114,7 +116,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     pdl_launch_dependents();
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
-    const int num_it = p.ntaps * p.kpt;
+    // split-K: blockIdx.z owns k-blocks [it0, it0 + num_it) of the taps x channel-chunks sequence
+    const int it0 = kSplit ? blockIdx.z * p.it_per_split : 0;
+    const int num_it = kSplit ? min(p.it_per_split, p.ntaps * p.kpt - it0) : p.ntaps * p.kpt;
 
     if (warp == 5) {
         // ------------------------------ B (weight) producer ------------------------------
@@ -127,7 +131,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (it >= p.stages) mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
             if (leader)
                 tma_load_2d(smem_base + stage * p.stage_stride + p.b_off, &tm_b, smem_u32(&bar_full[stage]),
-                            it * p.bk, ch0);
+                            (it0 + it) * p.bk, ch0);
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
@@ -169,24 +173,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (warp < 4) {
             const bool leader = elect_one();
             const uint32_t tx = p.a_bytes + p.b_bytes;
-            int stage = 0, it = 0;
+            int stage = 0, tap = it0 / p.kpt, kc = it0 - tap * p.kpt;
             uint32_t phase = 0;
-            for (int tap = 0; tap < p.ntaps; ++tap) {
-                const int4 t = s_tap[tap];
-                for (int kc = 0; kc < p.kpt; ++kc, ++it) {
-                    if ((stage & 3) == warp) {
-                        const uint32_t full = smem_u32(&bar_full[stage]);
-                        if (it >= p.stages) mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-                        if (leader) {
-                            mbar_expect_tx(full, tx);
-                            if (dbg && it < 16) dbg[24 + it] = clock64();
-                            tma_load_5d(smem_base + stage * p.stage_stride, &tm_a, full,
-                                        p.cin_coff + t.x + kc * p.bk, ow0 + t.y, t.z, oh0 + t.w, n0);
-                        }
-                        __syncwarp();
+            for (int it = 0; it < num_it; ++it) {
+                if ((stage & 3) == warp) {
+                    const int4 t = s_tap[tap];
+                    const uint32_t full = smem_u32(&bar_full[stage]);
+                    if (it >= p.stages) mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                    if (leader) {
+                        mbar_expect_tx(full, tx);
+                        if (dbg && it < 16) dbg[24 + it] = clock64();
+                        tma_load_5d(smem_base + stage * p.stage_stride, &tm_a, full,
+                                    p.cin_coff + t.x + kc * p.bk, ow0 + t.y, t.z, oh0 + t.w, n0);
                     }
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    __syncwarp();
                 }
+                if (++kc == p.kpt) { kc = 0; ++tap; }
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
         }
         // ---------------- epilogue: warps 0-3 and 6-9; TMEM lane quarter = warp % 4 ----------------
@@ -216,27 +219,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
             }
         };
-        fetch_res(chunk0);
-
-        mbar_wait(smem_u32(&bar_acc), 0);
-        if (dbg && threadIdx.x == 0) dbg[19] = clock64();
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        for (int c0 = chunk0; c0 < nvalid; c0 += 64) {
-            uint32_t v[32];
-            __syncwarp();   // tcgen05.ld is warp-aligned: reconverge after the predicated stores
-            tmem_ld_32(taddr + c0, v);
-            uint4 rcur[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-            if (c0 + 64 < nvalid) fetch_res(c0 + 64);
-            tmem_ld_wait();
-            if (dbg && threadIdx.x == 0 && c0 == chunk0) dbg[40] = clock64();
-            if (valid) {
+        // bias + SiLU + residual + store of one 32-column chunk held in f[]
+        auto finish_chunk = [&](int c0, float (&f)[32], const uint4 (&rcur)[4]) {
             const int cnt = min(32, nvalid - c0);
-            float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
+            for (int j = 0; j < 32; ++j) f[j] += s_bias[c0 + j];
             if (p.act) {
                 // SiLU, staged so that the 32 independent MUFU chains pipeline (ex2 pass, then rcp pass)
                 float e[32];
@@ -270,7 +257,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         if (j < cnt) f[j] += __half2float(rptr[c0 + j]);
                 }
             }
-            if (dbg && threadIdx.x == 0 && c0 == chunk0) dbg[41] = clock64() + (__float_as_int(f[0]) & 0);
             if (p.out_f32) {
                 float* o = static_cast<float*>(p.out) + pix * p.out_pitch + p.out_coff + ch0 + c0;
                 if (vec && (cnt & 3) == 0) {
@@ -302,8 +288,87 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         if (j < cnt) o[j] = __float2half_rn(f[j]);
                 }
             }
+        };
+
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        if (!kSplit) {
+            fetch_res(chunk0);
+            mbar_wait(smem_u32(&bar_acc), 0);
+            if (dbg && threadIdx.x == 0) dbg[19] = clock64();
+            tc_fence_after();
+            for (int c0 = chunk0; c0 < nvalid; c0 += 64) {
+                uint32_t v[32];
+                __syncwarp();   // tcgen05.ld is warp-aligned: reconverge after the predicated stores
+                tmem_ld_32(taddr + c0, v);
+                uint4 rcur[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+                if (c0 + 64 < nvalid) fetch_res(c0 + 64);
+                tmem_ld_wait();
+                if (dbg && threadIdx.x == 0 && c0 == chunk0) dbg[40] = clock64();
+                if (valid) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    finish_chunk(c0, f, rcur);
+                }
+                if (dbg && threadIdx.x == 0 && c0 == chunk0) dbg[42] = clock64();
             }
-            if (dbg && threadIdx.x == 0 && c0 == chunk0) dbg[42] = clock64();
+        } else {
+            // ---- split-K: every split parks its raw fp32 partial tile; the split that arrives last
+            // sums them in split order (deterministic) and runs the real epilogue ----
+            const size_t tile_lin = static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x;
+            float* part = p.partial + (tile_lin * p.splits * 128 + row) * p.part_ld;
+            const size_t split_stride = static_cast<size_t>(128) * p.part_ld;
+            mbar_wait(smem_u32(&bar_acc), 0);
+            if (dbg && threadIdx.x == 0) dbg[19] = clock64();
+            tc_fence_after();
+            for (int c0 = chunk0; c0 < nvalid; c0 += 64) {
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld_32(taddr + c0, v);
+                tmem_ld_wait();
+                if (valid) {
+                    float4* o = reinterpret_cast<float4*>(part + blockIdx.z * split_stride + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                }
+            }
+            if (dbg && threadIdx.x == 0) dbg[43] = clock64();
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps: all partial stores issued
+            if (threadIdx.x == 0) {
+                __threadfence();   // cumulative: publishes the CTA's stores ordered before it by the barrier
+                s_last = (atomicAdd(p.counters + tile_lin, 1) == p.splits - 1) ? 1 : 0;
+                __threadfence();
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (dbg && threadIdx.x == 0) dbg[44] = clock64();
+            if (s_last) {
+                fetch_res(chunk0);
+                for (int c0 = chunk0; c0 < nvalid; c0 += 64) {
+                    uint4 rcur[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+                    if (c0 + 64 < nvalid) fetch_res(c0 + 64);
+                    if (valid) {
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = 0.f;
+                        for (int z = 0; z < p.splits; ++z) {
+                            const float4* src = reinterpret_cast<const float4*>(part + z * split_stride + c0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 t = __ldcg(src + j);
+                                f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+                            }
+                        }
+                        finish_chunk(c0, f, rcur);
+                    }
+                }
+                if (threadIdx.x == 0) p.counters[tile_lin] = 0;   // ready for the next launch of this layer
+            }
         }
         __syncwarp();
         if (dbg && threadIdx.x == 0) dbg[20] = clock64();
@@ -365,54 +430,73 @@ __global__ void conv_simt_kernel(ConvDesc d) {
     }
 }
 
-// Stem: 3x3 stride-2, Cin = 3 (stored as 4), all Cout (<= 32) per thread, weights in shared memory.
+// Stem: 3x3 stride-2, Cin = 3 (stored as 4).  One thread = two horizontally adjacent output pixels x
+// all COUT channels: the 3x5 input patch lives in registers, each (cout, tap) weight triple is one
+// broadcast LDS.128 feeding 6 FMAs.
 template <int COUT>
 __global__ void __launch_bounds__(128) conv_stem_kernel(ConvDesc d) {
-    __shared__ float ws[COUT * 36];
+    __shared__ float4 ws[COUT * 9];
     __shared__ float bs[COUT];
-    for (int i = threadIdx.x; i < COUT * 36; i += blockDim.x) ws[i] = __half2float(d.w[i]);
+    for (int i = threadIdx.x; i < COUT * 9; i += blockDim.x) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(d.w + static_cast<size_t>(i) * 4);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        ws[i] = make_float4(a.x, a.y, b.x, 0.f);
+    }
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = d.bias[i];
     __syncthreads();
-    const long total = static_cast<long>(d.n) * d.h_out * d.w_out;
-    const long pix = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (pix >= total) return;
-    const int ow = static_cast<int>(pix % d.w_out);
-    const int oh = static_cast<int>((pix / d.w_out) % d.h_out);
-    const int n = static_cast<int>(pix / (static_cast<long>(d.w_out) * d.h_out));
-    float x[36];
+    const int wpairs = (d.w_out + 1) / 2;
+    const long total = static_cast<long>(d.n) * d.h_out * wpairs;
+    const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ox = static_cast<int>(idx % wpairs) * 2;
+    const int oy = static_cast<int>((idx / wpairs) % d.h_out);
+    const int n = static_cast<int>(idx / (static_cast<long>(wpairs) * d.h_out));
+    float x[3][5][3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
+        const int iy = oy * 2 - 1 + r;
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            const int ih = oh * 2 - 1 + r, iw = ow * 2 - 1 + s;
+        for (int c = 0; c < 5; ++c) {
+            const int ix = ox * 2 - 1 + c;
             uint2 raw = make_uint2(0u, 0u);
-            if (ih >= 0 && ih < d.h_in && iw >= 0 && iw < d.w_in)
-                raw = *reinterpret_cast<const uint2*>(d.in + ((static_cast<size_t>(n) * d.h_in + ih) * d.w_in + iw) * 4);
+            if (iy >= 0 && iy < d.h_in && ix >= 0 && ix < d.w_in)
+                raw = __ldg(reinterpret_cast<const uint2*>(d.in + ((static_cast<size_t>(n) * d.h_in + iy) * d.w_in + ix) * 4));
             const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
             const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-            x[(r * 3 + s) * 4 + 0] = a.x; x[(r * 3 + s) * 4 + 1] = a.y;
-            x[(r * 3 + s) * 4 + 2] = b.x; x[(r * 3 + s) * 4 + 3] = b.y;
+            x[r][c][0] = a.x; x[r][c][1] = a.y; x[r][c][2] = b.x;
         }
     }
-    __half* o = static_cast<__half*>(d.out) + pix * d.out_pitch + d.out_coff;
+    const bool second = ox + 1 < d.w_out;
+    const size_t pix = (static_cast<size_t>(n) * d.h_out + oy) * d.w_out + ox;
+    __half* o0 = static_cast<__half*>(d.out) + pix * d.out_pitch + d.out_coff;
+    __half* o1 = o0 + d.out_pitch;
 #pragma unroll
     for (int c0 = 0; c0 < COUT; c0 += 8) {
-        uint4 pack;
-        __half2* hp = reinterpret_cast<__half2*>(&pack);
+        float y0[8], y1[8];
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-            float y[2];
+        for (int j = 0; j < 8; ++j) {
+            float a0 = bs[c0 + j], a1 = a0;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                float acc = bs[c0 + j + u];
-                const float* w = ws + (c0 + j + u) * 36;
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int i = 0; i < 36; ++i) acc = fmaf(x[i], w[i], acc);
-                y[u] = __fdividef(acc, 1.0f + __expf(-acc));
-            }
-            hp[j / 2] = __floats2half2_rn(y[0], y[1]);
+                for (int t = 0; t < 3; ++t) {
+                    const float4 w = ws[(c0 + j) * 9 + r * 3 + t];
+                    a0 = fmaf(x[r][t][0], w.x, a0); a0 = fmaf(x[r][t][1], w.y, a0); a0 = fmaf(x[r][t][2], w.z, a0);
+                    a1 = fmaf(x[r][t + 2][0], w.x, a1); a1 = fmaf(x[r][t + 2][1], w.y, a1); a1 = fmaf(x[r][t + 2][2], w.z, a1);
+                }
+            y0[j] = a0; y1[j] = a1;
         }
-        *reinterpret_cast<uint4*>(o + c0) = pack;
+        uint4 p0, p1;
+        __half2* h0 = reinterpret_cast<__half2*>(&p0);
+        __half2* h1 = reinterpret_cast<__half2*>(&p1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h0[j] = __floats2half2_rn(silu(y0[2 * j]), silu(y0[2 * j + 1]));
+            h1[j] = __floats2half2_rn(silu(y1[2 * j]), silu(y1[2 * j + 1]));
+        }
+        *reinterpret_cast<uint4*>(o0 + c0) = p0;
+        if (second) *reinterpret_cast<uint4*>(o1 + c0) = p1;
     }
 }
 
@@ -449,6 +533,57 @@ __global__ void maxpool5_kernel(const __half* in, int in_pitch, int in_coff, __h
 #pragma unroll
     for (int j = 0; j < 4; ++j) ho[j] = m[j];
     *reinterpret_cast<uint4*>(out + pix * out_pitch + out_coff + g * 8) = o;
+}
+
+// SPPF: y1 = maxpool5(x), y2 = maxpool5(y1), y3 = maxpool5(y2) in one launch.  One block per
+// (image, 8-channel group): the H x W x 8 slab stays in shared memory, each pool is a separable
+// 5-max (row pass, column pass); the three results go to their channel offsets of the concat buffer.
+__global__ void __launch_bounds__(256) sppf_pool3_kernel(const __half* in, int in_pitch, int in_coff, __half* out,
+                                                         int out_pitch, int coff1, int coff2, int coff3, int h, int w) {
+    extern __shared__ uint4 sp_smem[];
+    uint4* cur = sp_smem;
+    uint4* tmp = sp_smem + h * w;
+    const int g = blockIdx.x, b = blockIdx.y, hw = h * w;
+    const size_t base = static_cast<size_t>(b) * hw;
+    for (int i = threadIdx.x; i < hw; i += blockDim.x)
+        cur[i] = *reinterpret_cast<const uint4*>(in + (base + i) * in_pitch + in_coff + g * 8);
+    __syncthreads();
+    const int coffs[3] = {coff1, coff2, coff3};
+    for (int round = 0; round < 3; ++round) {
+        for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+            const int x = i % w, y = i / w;
+            uint4 m = cur[i];
+            __half2* hm = reinterpret_cast<__half2*>(&m);
+#pragma unroll
+            for (int dx = -2; dx <= 2; ++dx) {
+                const int xx = x + dx;
+                if (dx == 0 || xx < 0 || xx >= w) continue;
+                const uint4 v = cur[y * w + xx];
+                const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hm[j] = __hmax2(hm[j], hv[j]);
+            }
+            tmp[i] = m;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+            const int x = i % w, y = i / w;
+            uint4 m = tmp[i];
+            __half2* hm = reinterpret_cast<__half2*>(&m);
+#pragma unroll
+            for (int dy = -2; dy <= 2; ++dy) {
+                const int yy = y + dy;
+                if (dy == 0 || yy < 0 || yy >= h) continue;
+                const uint4 v = tmp[yy * w + x];
+                const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hm[j] = __hmax2(hm[j], hv[j]);
+            }
+            *reinterpret_cast<uint4*>(out + (base + i) * out_pitch + coffs[round] + g * 8) = m;
+            cur[i] = m;   // each thread rewrites only its own pixels; readers of `cur` wait at the barrier below
+        }
+        __syncthreads();
+    }
 }
 
 __global__ void upsample2_kernel(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch,
@@ -504,6 +639,18 @@ void encode(CUtensorMap* tm, void* base, int rank, const cuuint64_t* dims, const
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+}
+
+// Split-K is implemented (deterministic: fp32 partial tiles, last-arriving split reduces in split
+// order) but OFF by default: on B200 it halves the per-CTA lifetime of the 20x20 / 10x10 layers yet
+// leaves the graph replay time unchanged (car 0.445 ms with, 0.436 ms without; profiles/r1_summary.md),
+// because those layers already overlap with other graph branches.  RMR_SPLITK=1 turns it on.
+bool split_k_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("RMR_SPLITK");
+        return e && e[0] == '1';
+    }();
+    return on;
 }
 
 // Output-channel tile: the widest divisor of cout_pad (multiple of 16, <= 128) that still yields at
@@ -563,6 +710,23 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
     p.stage_stride = p.a_bytes + p.b_bytes;
     p.stages = std::max(1, std::min({kMaxStages, static_cast<int>(kSmemBudget / p.stage_stride), p.ntaps * p.kpt}));
     p.tmem_cols = p.block_n <= 32 ? 32u : p.block_n <= 64 ? 64u : 128u;
+    // split-K: a layer whose tiles cover less than half the SMs but whose K loop is long is cut along K;
+    // each split keeps at least 3 k-blocks
+    {
+        const long ctas = static_cast<long>(p.tiles_w) * p.tiles_h * p.tiles_n * (d.cout_pad / p.block_n);
+        const int num_it = p.ntaps * p.kpt;
+        int splits = 1;
+        if (split_k_enabled() && ctas * 3 <= 148 && num_it >= 16) {
+            const int want = static_cast<int>(std::min<long>(16, 148 / ctas));
+            const int ips = std::max(4, (num_it + want - 1) / want);
+            splits = (num_it + ips - 1) / ips;
+            p.it_per_split = ips;
+        }
+        if (splits <= 2) { splits = 1; p.it_per_split = num_it; }   // two-way splits do not pay for the extra sync
+        p.splits = splits;
+        p.stages = std::max(1, std::min(p.stages, p.it_per_split));
+        p.part_ld = (p.block_n + 31) / 32 * 32;
+    }
     const int out_align = d.out_f32 ? 4 : 8;
     p.vec_ok = (d.out_pitch % out_align == 0 && d.out_coff % out_align == 0 &&
                 (d.res == nullptr || (d.res_pitch % 8 == 0 && d.res_coff % 8 == 0))) ? 1 : 0;
@@ -603,7 +767,7 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
         cuuint32_t box[2] = {static_cast<cuuint32_t>(p.bk), static_cast<cuuint32_t>(p.block_n)};
         encode(&l.tm_b, const_cast<__half*>(d.w), 2, dims, strides, box, swz);
     }
-    l.grid = dim3(p.tiles_w * p.tiles_h * p.tiles_n, d.cout_pad / p.block_n, 1);
+    l.grid = dim3(p.tiles_w * p.tiles_h * p.tiles_n, d.cout_pad / p.block_n, p.splits);
     l.smem_bytes = p.stages * static_cast<int>(p.stage_stride) + 1024;
     l.flops = 2.0 * d.n * d.h_out * d.w_out * static_cast<double>(d.cout) * d.k * d.k * d.cin;
     return l;
@@ -611,12 +775,32 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
 
 static bool g_use_pdl = true;
 
+// scratch of a split-K launch: one arrival counter per output tile (zero between launches), then the
+// fp32 partial tiles [tile][split][128][part_ld]
+size_t conv_scratch_bytes(const ConvLaunch& l) {
+    if (l.p.splits <= 1) return 0;
+    const size_t tiles = static_cast<size_t>(l.grid.x) * l.grid.y;
+    return (tiles * sizeof(int) + 255) / 256 * 256 + tiles * l.p.splits * 128 * l.p.part_ld * sizeof(float);
+}
+
+void conv_bind_scratch(ConvLaunch& l, void* zeroed_base) {
+    if (l.p.splits <= 1) return;
+    const size_t tiles = static_cast<size_t>(l.grid.x) * l.grid.y;
+    l.p.counters = static_cast<int*>(zeroed_base);
+    l.p.partial = reinterpret_cast<float*>(static_cast<char*>(zeroed_base) + (tiles * sizeof(int) + 255) / 256 * 256);
+}
+
+
 void conv_init() {
     static std::once_flag once;
     std::call_once(once, [] {
-        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kSmemBudget + 1024));
-        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kSmemBudget + 1024));
+        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       cudaSharedmemCarveoutMaxShared));
         get_encode_fn();
         const char* e = std::getenv("RMR_NO_PDL");
@@ -636,13 +820,14 @@ void launch_conv_umma(const ConvLaunch& l, cudaStream_t s, bool pdl) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (g_use_pdl && pdl) ? 1 : 0;
-    RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel, l.tm_a, l.tm_b, l.p));
+    if (l.p.splits > 1) RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<true>, l.tm_a, l.tm_b, l.p));
+    else RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<false>, l.tm_a, l.tm_b, l.p));
 }
 
 void launch_conv_simt(const ConvDesc& d, cudaStream_t s) {
     if (d.cin_pad == 4 && d.k == 3 && d.stride == 2 && d.act == 1 && d.res == nullptr && !d.out_f32 &&
         d.in_pitch == 4 && d.in_coff == 0 && (d.cout == 32 || d.cout == 16)) {
-        const long total = static_cast<long>(d.n) * d.h_out * d.w_out;
+        const long total = static_cast<long>(d.n) * d.h_out * ((d.w_out + 1) / 2);
         const int blocks = static_cast<int>((total + 127) / 128);
         if (d.cout == 32) conv_stem_kernel<32><<<blocks, 128, 0, s>>>(d);
         else conv_stem_kernel<16><<<blocks, 128, 0, s>>>(d);
@@ -658,6 +843,13 @@ void launch_maxpool5(const __half* in, int in_pitch, int in_coff, __half* out, i
     const long total = static_cast<long>(n) * h * w * (c / 8);
     maxpool5_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(in, in_pitch, in_coff, out, out_pitch,
                                                                           out_coff, n, h, w, c / 8);
+    RMR_CUDA(cudaGetLastError());
+}
+
+void launch_sppf_pool3(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch, int coff1, int coff2,
+                       int coff3, int n, int h, int w, int c, cudaStream_t s) {
+    sppf_pool3_kernel<<<dim3(c / 8, n), 256, static_cast<size_t>(2) * h * w * sizeof(uint4), s>>>(
+        in, in_pitch, in_coff, out, out_pitch, coff1, coff2, coff3, h, w);
     RMR_CUDA(cudaGetLastError());
 }
 

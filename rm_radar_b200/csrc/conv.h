@@ -34,6 +34,9 @@ struct ConvParams {
     uint32_t idesc, sbo, layout;
     uint32_t a_bytes, b_bytes, b_off, stage_stride, tmem_cols;   // operand ring geometry
     int stages, vec_ok;
+    int splits, it_per_split, part_ld;   // split-K: grid.z splits of it_per_split k-blocks; partial row pitch
+    float* partial;                      // [tile][split][128][part_ld] fp32 partial tiles
+    int* counters;                       // [tile] arrivals, zero between launches
     long long* dbg;                   // optional per-CTA clock64 timeline (64 slots per CTA), tests only
 };
 
@@ -48,12 +51,18 @@ struct ConvLaunch {
 void conv_init();   // one-time function attributes; must run outside stream capture
 bool conv_umma_supported(const ConvDesc& d);
 ConvLaunch make_conv_launch(const ConvDesc& d);
+// scratch a split-K launch needs (0 when the layer is not split); bind a zero-initialised region before launching
+size_t conv_scratch_bytes(const ConvLaunch& l);
+void conv_bind_scratch(ConvLaunch& l, void* zeroed_base);
 void launch_conv_umma(const ConvLaunch& l, cudaStream_t s, bool pdl = true);
 // generic direct convolution on CUDA cores: the stem (Cin=3) and the on-device checker for tests
 void launch_conv_simt(const ConvDesc& d, cudaStream_t s);
 
 void launch_maxpool5(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch, int out_coff,
                      int n, int h, int w, int c, cudaStream_t s);
+// SPPF's chained 5x5 max-pools (y1, y2, y3 -> three channel offsets of one buffer) in one launch; h*w <= 1024
+void launch_sppf_pool3(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch, int coff1, int coff2,
+                       int coff3, int n, int h, int w, int c, cudaStream_t s);
 void launch_upsample2(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch, int out_coff,
                       int n, int h_in, int w_in, int c, cudaStream_t s);
 void launch_copy_channels(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch, int out_coff,

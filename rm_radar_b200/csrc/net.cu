@@ -9,7 +9,8 @@ namespace rmr {
 
 namespace {
 constexpr char kMagic[8] = {'R', 'M', 'R', 'E', 'N', 'G', '2', '\0'};
-enum { OP_CONV = 0, OP_MAXPOOL5 = 1, OP_UPSAMPLE2 = 2, OP_COPY = 3 };
+enum { OP_CONV = 0, OP_MAXPOOL5 = 1, OP_UPSAMPLE2 = 2, OP_COPY = 3,
+       OP_SPPF3 = 100, OP_FUSED_AWAY = 101 };   // runtime-only step types (never in the engine file)
 
 struct Header {
     char magic[8];
@@ -74,8 +75,10 @@ Net::Net(const std::string& engine_path, int max_batch) : max_batch_(max_batch) 
 }
 
 Net::~Net() {
-    for (auto& kv : plans_)
+    for (auto& kv : plans_) {
         if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
+        cudaFree(kv.second.scratch);
+    }
     for (void* p : bufs_) cudaFree(p);
     cudaFree(weights_);
 }
@@ -110,6 +113,35 @@ Net::BatchPlan& Net::plan_for(int batch) {
         }
         bp.steps.push_back(st);
     }
+    // split-K scratch: every split layer gets its own region (layers on different graph lanes overlap)
+    size_t scratch = 0;
+    for (const Step& st : bp.steps)
+        if (st.umma) scratch += (conv_scratch_bytes(st.launch) + 255) / 256 * 256;
+    if (scratch > 0) {
+        RMR_CUDA(cudaMalloc(&bp.scratch, scratch));
+        RMR_CUDA(cudaMemset(bp.scratch, 0, scratch));
+        size_t off = 0;
+        for (Step& st : bp.steps)
+            if (st.umma) {
+                const size_t b = (conv_scratch_bytes(st.launch) + 255) / 256 * 256;
+                if (b) conv_bind_scratch(st.launch, static_cast<char*>(bp.scratch) + off);
+                off += b;
+            }
+    }
+    // SPPF: three chained 5x5 max-pools writing into one buffer -> a single launch
+    for (size_t i = 0; i + 2 < bp.steps.size(); ++i) {
+        const EngineOp &a = bp.steps[i].op, &b = bp.steps[i + 1].op, &c = bp.steps[i + 2].op;
+        if (a.type != OP_MAXPOOL5 || b.type != OP_MAXPOOL5 || c.type != OP_MAXPOOL5) continue;
+        const bool chained = b.src_buf == a.dst_buf && b.src_coff == a.dst_coff && c.src_buf == b.dst_buf &&
+                             c.src_coff == b.dst_coff && a.dst_buf == b.dst_buf && b.dst_buf == c.dst_buf &&
+                             a.src_c == b.src_c && b.src_c == c.src_c && a.src_h * a.src_w <= 1024 &&
+                             (a.src_c % 8) == 0;
+        if (!chained || force_simt_) continue;
+        bp.steps[i].type = OP_SPPF3;
+        bp.steps[i + 1].type = OP_FUSED_AWAY;
+        bp.steps[i + 2].type = OP_FUSED_AWAY;
+        bp.steps[i].sppf_coff[0] = a.dst_coff; bp.steps[i].sppf_coff[1] = b.dst_coff; bp.steps[i].sppf_coff[2] = c.dst_coff;
+    }
     schedule(bp);
     return plans_.emplace(batch, std::move(bp)).first->second;
 }
@@ -125,6 +157,13 @@ void Net::launch_step(const Step& st, int batch, cudaStream_t s, bool pdl) {
             launch_maxpool5(static_cast<const __half*>(bufs_[op.src_buf]), buf_desc_[op.src_buf].c, op.src_coff,
                             static_cast<__half*>(bufs_[op.dst_buf]), buf_desc_[op.dst_buf].c, op.dst_coff, batch,
                             op.src_h, op.src_w, op.src_c, s);
+            break;
+        case OP_SPPF3:
+            launch_sppf_pool3(static_cast<const __half*>(bufs_[op.src_buf]), buf_desc_[op.src_buf].c, op.src_coff,
+                              static_cast<__half*>(bufs_[op.dst_buf]), buf_desc_[op.dst_buf].c, st.sppf_coff[0],
+                              st.sppf_coff[1], st.sppf_coff[2], batch, op.src_h, op.src_w, op.src_c, s);
+            break;
+        case OP_FUSED_AWAY:
             break;
         case OP_UPSAMPLE2:
             launch_upsample2(static_cast<const __half*>(bufs_[op.src_buf]), buf_desc_[op.src_buf].c, op.src_coff,

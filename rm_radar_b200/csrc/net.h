@@ -54,7 +54,7 @@ public:
     std::vector<float> profile_ops(int batch, int iters, cudaStream_t s);
     bool op_uses_umma(int batch, int i) { return plan_for(batch).steps[i].umma; }
     // debugging / tests
-    void set_force_simt(bool v) { force_simt_ = v; plans_.clear(); }
+    void set_force_simt(bool v) { force_simt_ = v; }
     void set_use_graph(bool v) { use_graph_ = v; }
     const void* buffer(int i) const { return bufs_[i]; }
     const EngineBuf& buffer_desc(int i) const { return buf_desc_[i]; }
@@ -68,6 +68,7 @@ private:
         ConvDesc desc;
         ConvLaunch launch;
         EngineOp op;
+        int sppf_coff[3] = {0, 0, 0};   // OP_SPPF3: channel offsets of y1, y2, y3
         int lane = 0;               // capture stream this op is recorded on (independent branches overlap)
         std::vector<int> deps;      // ops on other lanes that must finish first (RAW / WAR / WAW on buffer views)
         bool signals = false;       // some op on another lane depends on this one
@@ -76,6 +77,7 @@ private:
         std::vector<Step> steps;
         cudaGraphExec_t graph = nullptr;
         int lanes = 1;
+        void* scratch = nullptr;   // split-K counters + partial tiles
     };
     BatchPlan& plan_for(int batch);
     void run_steps(const BatchPlan& bp, int batch, cudaStream_t s);

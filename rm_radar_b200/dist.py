@@ -1,0 +1,57 @@
+"""Multi-GPU plumbing: one process per GPU, one camera + LiDAR stream per rank.
+
+The hot path shards by stream with no data-path collective; the only exchange is the fixed-size block
+of world-frame robot records every rank publishes once per step (the reference has no distributed
+code at all).  `torch.distributed` is the transport: NCCL over NVLink on the GPU box, gloo in the CPU
+tests.  Record layout (8 float32 per robot, `max_cars` rows per rank):
+    [valid, label (-1 = undetected), confidence, is_located, x, y, z (metres, world), rect area]
+"""
+from __future__ import annotations
+
+import torch
+
+RECORD_FLOATS = 8
+
+
+def pack_records(recs, n: int, max_cars: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """ctypes RobotRec array (or any objects with the same fields) -> [max_cars, 8] float32 CPU tensor."""
+    if out is None:
+        out = torch.zeros(max_cars, RECORD_FLOATS)
+    else:
+        out.zero_()
+    for i in range(min(n, max_cars)):
+        r = recs[i]
+        out[i, 0] = 1.0
+        out[i, 1] = float(r.label) if r.is_detected else -1.0
+        out[i, 2] = float(r.confidence)
+        out[i, 3] = float(r.is_located)
+        if r.is_located:
+            out[i, 4] = r.location[0]; out[i, 5] = r.location[1]; out[i, 6] = r.location[2]
+        out[i, 7] = float(r.rect[2]) * float(r.rect[3])
+    return out
+
+
+def all_gather_records(block: torch.Tensor, gathered: torch.Tensor | None = None, group=None) -> torch.Tensor:
+    """One collective per step: every rank's [max_cars, 8] block -> [world, max_cars, 8] on every rank."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if gathered is None:
+        gathered = torch.empty(world * block.shape[0], block.shape[1], dtype=block.dtype, device=block.device)
+    dist.all_gather_into_tensor(gathered, block.contiguous(), group=group)
+    return gathered.view(world, block.shape[0], block.shape[1])
+
+
+def unpack_records(gathered: torch.Tensor):
+    """[world, max_cars, 8] -> list (per rank) of dicts for the valid robots, in record order."""
+    out = []
+    g = gathered.cpu()
+    for rank in range(g.shape[0]):
+        robots = []
+        for row in g[rank]:
+            if row[0] < 0.5:
+                continue
+            robots.append(dict(label=int(row[1]), confidence=float(row[2]),
+                               location=tuple(float(v) for v in row[4:7]) if row[3] > 0.5 else None,
+                               area=float(row[7])))
+        out.append(robots)
+    return out

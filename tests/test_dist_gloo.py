@@ -1,0 +1,58 @@
+"""CPU, world_size 2, gloo: the N>1 plumbing of bench.py — per-rank robot record blocks, one
+all-gather per step, every rank ends up with every stream's robots in rank order."""
+import os
+import socket
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rm_radar_b200 import dist as rdist
+
+MAX_CARS = 20
+
+
+def fake_recs(rank):
+    """Deterministic per-rank robots shaped like the C ABI's rmr_robot_t."""
+    recs = []
+    for i in range(3 + rank):
+        located = (i + rank) % 2 == 0
+        recs.append(SimpleNamespace(label=(5 * rank + i) % 12, is_detected=int(i != 1), confidence=0.5 + 0.01 * i,
+                                    is_located=int(located), location=(1.0 * rank + i, 2.0, 0.5 * i),
+                                    rect=(10.0, 20.0, 30.0 + i, 40.0)))
+    return recs
+
+
+def worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        recs = fake_recs(rank)
+        block = rdist.pack_records(recs, len(recs), MAX_CARS)
+        assert block.shape == (MAX_CARS, rdist.RECORD_FLOATS) and block[len(recs):].abs().sum() == 0
+        for _ in range(3):      # one collective per step, buffers reused
+            gathered = rdist.all_gather_records(block)
+        assert gathered.shape == (world, MAX_CARS, rdist.RECORD_FLOATS)
+        per_rank = rdist.unpack_records(gathered)
+        for r in range(world):
+            want = fake_recs(r)
+            assert len(per_rank[r]) == len(want)
+            for got, w in zip(per_rank[r], want):
+                assert got["label"] == (w.label if w.is_detected else -1)
+                assert (got["location"] is not None) == bool(w.is_located)
+                if w.is_located:
+                    assert got["location"] == pytest.approx(w.location)
+        # capacity: more robots than max_cars are truncated, never overflow the block
+        many = fake_recs(0) * 10
+        assert rdist.pack_records(many, len(many), MAX_CARS).shape[0] == MAX_CARS
+    finally:
+        dist.destroy_process_group()
+
+
+def test_all_gather_of_robot_records_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(worker, args=(2, port), nprocs=2, join=True)

@@ -3,8 +3,11 @@
 import numpy as np
 import rm_radar_b200 as rr
 
+import sys
 SHAPES = [(1, 160, 160, 64, 64, 3, 1), (1, 160, 160, 64, 1, 1, 1), (1, 20, 20, 512, 64, 3, 1), (1, 40, 40, 128, 128, 3, 1),
           (7, 80, 80, 128, 128, 3, 1)]
+if len(sys.argv) > 1:
+    SHAPES = [tuple(int(v) for v in a.split(',')) for a in sys.argv[1:]]
 for sh in SHAPES:
     t = rr.conv_timeline(*sh)
     n = len(t)
@@ -15,6 +18,6 @@ for sh in SHAPES:
         r = d[c]
         nit = int(np.sum(t[c, 2:18] != 0))
         print(f" cta {c}: setup {r[1]}, full[it] {[int(x) for x in r[2:2 + nit]]}, mma_issued {r[18]}, acc_ready {r[19]}, "
-              f"epi_done {r[20]}, exit {r[21]}; tma_issue[it] {[int(x) for x in r[24:24 + nit]]}; epi chunk0: ld_done {r[40]} computed {r[41]} stored {r[42]}")
+              f"epi_done {r[20]}, exit {r[21]}; tma_issue[it] {[int(x) for x in r[24:24 + nit]]}; epi chunk0: ld_done {r[40]} stored {r[42]}; split: dumped {r[43]} synced {r[44]}")
     med = np.median(d, axis=0)
     print(f" median: setup {med[1]:.0f} first_full {med[2]:.0f} mma_issued {med[18]:.0f} acc_ready {med[19]:.0f} epi_done {med[20]:.0f} exit {med[21]:.0f}")
