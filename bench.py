@@ -187,8 +187,12 @@ def run_ours(args, rank, world, local_rank):
     det = rr.RobotDetector(fx.engine("car"), fx.engine("armor"), (W, H), fx.CLASS_NUM, fx.MAX_BATCH, fx.OPT_BATCH,
                            device=local_rank)
     loc = rr.Locator(W, H, fx.scaled_intrinsic(W, H), fx.LIDAR_TO_CAMERA, fx.WORLD_TO_CAMERA, device=local_rank)
+    # detect runs on the timed stream; the Locator keeps its own stream, so update + cluster overlap with
+    # detect exactly like the reference's two std::async threads (sample_radar.h:107-114).  search()
+    # synchronises the locator stream before it returns, so the closing event covers both.
     det.set_stream(stream.cuda_stream)
-    loc.set_stream(stream.cuda_stream)
+    loc_stream = torch.cuda.Stream(device=dev)
+    loc.set_stream(loc_stream.cuda_stream)
     loc.update(bg[: 1 << 20])
 
     # HBM-resident pool (value) and pinned host pool (e2e)
@@ -212,6 +216,7 @@ def run_ours(args, rank, world, local_rank):
 
     def step_resident(i):
         j = i % POOL
+        loc_stream.wait_stream(stream)      # the cloud of step i is not touched before step i-1 is done
         loc.update_device(clouds_dev[j].data_ptr(), NPTS, 12)
         loc.cluster()
         recs, n = det.detect_records(frames_dev[j].data_ptr(), W, H, W * 3, device_ptr=True)
@@ -221,6 +226,7 @@ def run_ours(args, rank, world, local_rank):
 
     def step_e2e(i):
         j = i % POOL
+        loc_stream.wait_stream(stream)
         _lib.check(lib.rmr_locator_update(loc._h, ctypes.c_void_p(clouds_pin[j].data_ptr()), NPTS, 12))
         loc.cluster()
         recs, n = det.detect_records(frames_pin[j].data_ptr(), W, H, W * 3, device_ptr=False)

@@ -1,5 +1,6 @@
 // extern "C" boundary (include/rm_radar_b200.h).  Exceptions become status codes + a thread-local
 // message; nothing here computes on the CPU.
+#include <cstdlib>
 #include <cstring>
 #include <random>
 
@@ -479,6 +480,7 @@ int rmr_conv_timeline(int n, int h_in, int w_in, int cin, int cout, int k, int s
         RMR_CUDA(cudaStreamCreate(&s));
         for (int i = 0; i < 3; ++i) launch_conv_umma(l, s);
         l.p.dbg = d_dbg;
+        if (const char* f = std::getenv("RMR_DBG_FLAGS")) l.p.dbg_flags = std::atoi(f);
         launch_conv_umma(l, s);
         RMR_CUDA(cudaStreamSynchronize(s));
         *n_ctas = ctas;

@@ -34,9 +34,11 @@ struct ConvParams {
     uint32_t idesc, sbo, layout;
     uint32_t a_bytes, b_bytes, b_off, stage_stride, tmem_cols;   // operand ring geometry
     int stages, vec_ok;
+    int halo, na;                        // halo mode (3x3 stride 1): on/off, activation patch slots (1 or 2)
     int splits, it_per_split, part_ld;   // split-K: grid.z splits of it_per_split k-blocks; partial row pitch
     float* partial;                      // [tile][split][128][part_ld] fp32 partial tiles
     int* counters;                       // [tile] arrivals, zero between launches
+    int dbg_flags;                    // profiling only: bit0 = issue no MMAs, bit1 = one k-step per k-block
     long long* dbg;                   // optional per-CTA clock64 timeline (64 slots per CTA), tests only
 };
 

@@ -18,6 +18,6 @@ for sh in SHAPES:
         r = d[c]
         nit = int(np.sum(t[c, 2:18] != 0))
         print(f" cta {c}: setup {r[1]}, full[it] {[int(x) for x in r[2:2 + nit]]}, mma_issued {r[18]}, acc_ready {r[19]}, "
-              f"epi_done {r[20]}, exit {r[21]}; tma_issue[it] {[int(x) for x in r[24:24 + nit]]}; epi chunk0: ld_done {r[40]} stored {r[42]}; split: dumped {r[43]} synced {r[44]}")
+              f"epi_done {r[20]}, exit {r[21]}; tma_issue[it] {[int(x) for x in r[24:24 + nit]]}; epi chunk0: ld_done {r[40]} stored {r[42]}; mma pre-wait {[int(x) for x in r[44:44 + min(nit, 10)]]}; B issue {[int(x) for x in r[54:54 + min(nit, 10)]]}")
     med = np.median(d, axis=0)
     print(f" median: setup {med[1]:.0f} first_full {med[2]:.0f} mma_issued {med[18]:.0f} acc_ready {med[19]:.0f} epi_done {med[20]:.0f} exit {med[21]:.0f}")
