@@ -268,6 +268,7 @@ def run_ours(args, rank, world, local_rank):
     car_ms = det.car_detector().time_forward(1, 20)
     armor_ms = det.armor_detector().time_forward(max(k_cars, 1), 20) if k_cars else 0.0
     conv_ms = car_ms + armor_ms
+    conv_launches = det.car_detector().plan_stats(1)["umma_convs"] + (det.armor_detector().plan_stats(k_cars)["umma_convs"] if k_cars else 0)
     peak_tf, peak_hbm, peak_src = peaks()
     achieved_tf = stats["conv_flops"] / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
 
@@ -290,6 +291,10 @@ def run_ours(args, rank, world, local_rank):
                      "frac": achieved_tf / peak_tf, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "kernel": "conv_umma_kernel (tcgen05 implicit GEMM), all conv launches of one frame",
                      "flops_per_step": stats["conv_flops"], "conv_ms_per_step": conv_ms,
+                     "conv_launches_per_step": conv_launches,
+                     "flops_per_launch": stats["conv_flops"] / max(conv_launches, 1),
+                     "avg_launch_us": 1e3 * conv_ms / max(conv_launches, 1),
+                     "traffic_note": "mean dram__bytes_read+write per launch, ncu --set full, profiles/r1_conv_full.json",
                      "car_net_ms": car_ms, "armor_net_ms": armor_ms, "armor_batch": k_cars,
                      "conv_share_of_step": conv_ms / (ms_res / args.steps),
                      "frac_of_conv_bound_frames_per_s": (value / world) / (peak_tf * 1e12 / stats["conv_flops"])},

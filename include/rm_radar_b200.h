@@ -80,6 +80,8 @@ int rmr_detector_detect_batch(rmr_detector_t* d, const uint8_t* const* bgr, cons
 int rmr_detector_last_input(rmr_detector_t* d, float* out, int n_images);
 int rmr_detector_last_output(rmr_detector_t* d, float* out, int n_images);
 int rmr_detector_info(rmr_detector_t* d, int* anchors, int* classes, int* kernel_launches, double* flops_per_image);
+/* plan of the network at `batch`: launches per forward, tcgen05 conv launches among them, parallel graph lanes */
+int rmr_detector_plan_stats(rmr_detector_t* d, int batch, int* launches, int* umma_convs, int* graph_lanes);
 int rmr_detector_set_stream(rmr_detector_t* d, void* cuda_stream);
 /* bench: replays the network (the captured conv-stack graph) `iters` times at `batch` on the
  * detector's stream, timed with CUDA events on that stream; ms = average per replay */

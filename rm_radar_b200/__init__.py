@@ -187,6 +187,11 @@ class Detector:
         keys = ("type", "umma", "h_in", "w_in", "cin", "h_out", "w_out", "cout", "k", "stride", "flops", "ms")
         return [dict(zip(keys, rows[i].tolist())) for i in range(min(n.value, cap))]
 
+    def plan_stats(self, batch: int = 1):
+        n, u, l = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(self._lib.rmr_detector_plan_stats(self._h, batch, C.byref(n), C.byref(u), C.byref(l)))
+        return dict(launches=n.value, umma_convs=u.value, graph_lanes=l.value)
+
     def info(self):
         a, c, k, f = C.c_int(), C.c_int(), C.c_int(), C.c_double()
         _lib.check(self._lib.rmr_detector_info(self._h, C.byref(a), C.byref(c), C.byref(k), C.byref(f)))

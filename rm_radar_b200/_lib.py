@@ -31,7 +31,7 @@ SYMBOLS = [
     "rmr_last_error", "rmr_device_count",
     "rmr_detector_create", "rmr_detector_destroy", "rmr_detector_detect", "rmr_detector_detect_batch",
     "rmr_detector_last_input", "rmr_detector_last_output", "rmr_detector_info", "rmr_detector_set_stream",
-    "rmr_detector_time_forward", "rmr_detector_profile_ops",
+    "rmr_detector_time_forward", "rmr_detector_profile_ops", "rmr_detector_plan_stats",
     "rmr_robot_detector_create", "rmr_robot_detector_destroy", "rmr_robot_detector_detect",
     "rmr_robot_detector_detect_device", "rmr_robot_detector_last_cars", "rmr_robot_detector_last_armors",
     "rmr_robot_detector_set_stream", "rmr_robot_detector_last_stats", "rmr_robot_detector_car",
@@ -72,6 +72,7 @@ def load():
     lib.rmr_detector_info.argtypes = [vp, P(ci), P(ci), P(ci), P(cd)]
     lib.rmr_detector_set_stream.argtypes = [vp, vp]
     lib.rmr_detector_time_forward.argtypes = [vp, ci, ci, P(cf)]
+    lib.rmr_detector_plan_stats.argtypes = [vp, ci, P(ci), P(ci), P(ci)]
     lib.rmr_detector_profile_ops.argtypes = [vp, ci, ci, P(cd), ci, P(ci)]
     lib.rmr_robot_detector_create.argtypes = [P(vp), C.c_char_p, C.c_char_p, ci, ci, ci, ci, cf, cf, cf, cf, cf,
                                               ci, ci, ci, ci]

@@ -121,6 +121,13 @@ int rmr_detector_info(rmr_detector_t* d, int* anchors, int* classes, int* kernel
         if (flops_per_image) *flops_per_image = d->impl->net().flops_per_image();
     });
 }
+int rmr_detector_plan_stats(rmr_detector_t* d, int batch, int* launches, int* umma_convs, int* graph_lanes) {
+    return guarded([&] {
+        if (!d) throw std::invalid_argument("null argument");
+        RMR_CUDA(cudaSetDevice(d->impl->device()));
+        d->impl->net().plan_stats(batch, launches, umma_convs, graph_lanes);
+    });
+}
 int rmr_detector_set_stream(rmr_detector_t* d, void* cuda_stream) {
     return guarded([&] { d->impl->set_stream(static_cast<cudaStream_t>(cuda_stream)); });
 }

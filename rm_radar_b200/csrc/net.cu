@@ -304,6 +304,20 @@ void Net::capture(BatchPlan& bp, int batch) {
     cleanup();
 }
 
+void Net::plan_stats(int batch, int* launches, int* umma_convs, int* lanes) {
+    if (batch <= 0 || batch > max_batch_) throw std::invalid_argument("plan_stats: bad batch");
+    const BatchPlan& bp = plan_for(batch);
+    int nl = 0, nu = 0;
+    for (const Step& st : bp.steps) {
+        if (st.type == OP_FUSED_AWAY) continue;
+        ++nl;
+        if (st.type == OP_CONV && st.umma) ++nu;
+    }
+    if (launches) *launches = nl;
+    if (umma_convs) *umma_convs = nu;
+    if (lanes) *lanes = bp.lanes;
+}
+
 void Net::run_one(const Step& st, int batch, cudaStream_t s) {
     BatchPlan one;
     one.steps.push_back(st);

@@ -52,6 +52,7 @@ public:
     int launches_per_forward() const { return static_cast<int>(ops_.size()); }
     // per-op timing (bench / profiling): ms per launch of every op at `batch`, `iters` back-to-back launches each
     std::vector<float> profile_ops(int batch, int iters, cudaStream_t s);
+    void plan_stats(int batch, int* launches, int* umma_convs, int* lanes);
     bool op_uses_umma(int batch, int i) { return plan_for(batch).steps[i].umma; }
     // debugging / tests
     void set_force_simt(bool v) { force_simt_ = v; }
