@@ -515,6 +515,7 @@ Locator::Locator(const LocatorConfig& cfg, int max_points, int max_foreground, i
 
     RMR_CUDA(cudaMalloc(&cloud_, sizeof(float) * 4 * max_points_));
     RMR_CUDA(cudaMallocHost(&pinned_cloud_, sizeof(float) * 4 * max_points_));
+    RMR_CUDA(cudaEventCreateWithFlags(&cloud_uploaded_, cudaEventDisableTiming));
     RMR_CUDA(cudaMalloc(&packed_, sizeof(unsigned long long) * npix_));
     RMR_CUDA(cudaMalloc(&bg_, sizeof(float) * npix_));
     RMR_CUDA(cudaMalloc(&diff_, sizeof(float) * npix_));
@@ -540,7 +541,8 @@ Locator::Locator(const LocatorConfig& cfg, int max_points, int max_foreground, i
 }
 
 Locator::~Locator() {
-    cudaFree(cloud_); cudaFreeHost(pinned_cloud_); cudaFree(packed_); cudaFree(bg_); cudaFree(diff_);
+    cudaFree(cloud_); cudaFreeHost(pinned_cloud_);
+    if (cloud_uploaded_) cudaEventDestroy(cloud_uploaded_); cudaFree(packed_); cudaFree(bg_); cudaFree(diff_);
     cudaFree(ring_); cudaFree(label_img_); cudaFree(block_counts_); cudaFree(block_offsets_); cudaFree(counters_);
     cudaFree(fg_pts_); cudaFree(parent_); cudaFree(next_); cudaFree(heads_); cudaFree(cell_keys_); cudaFree(comp_size_);
     cudaFree(cluster_id_); cudaFree(root_list_); cudaFree(hist_); cudaFree(dev_rects_); cudaFree(dev_results_);
@@ -569,7 +571,9 @@ void Locator::update_host(const float* points, int n, int stride_floats, cudaStr
         return;
     }
     if (n > max_points_) throw std::invalid_argument("Locator::update: cloud larger than max_points");
-    // pack xyz to 3 floats while staging through pinned memory (PointXYZ has a padding float)
+    // pack xyz to 3 floats while staging through pinned memory (PointXYZ has a padding float); the
+    // previous upload must have left the staging buffer before it is rewritten
+    RMR_CUDA(cudaEventSynchronize(cloud_uploaded_));
     if (stride_floats == 3) {
         std::memcpy(pinned_cloud_, points, sizeof(float) * 3 * n);
     } else {
@@ -580,6 +584,7 @@ void Locator::update_host(const float* points, int n, int stride_floats, cudaStr
         }
     }
     RMR_CUDA(cudaMemcpyAsync(cloud_, pinned_cloud_, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, s));
+    RMR_CUDA(cudaEventRecord(cloud_uploaded_, s));
     update_device(cloud_, n, 3, s);
 }
 

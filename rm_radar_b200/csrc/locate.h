@@ -77,6 +77,7 @@ private:
     int nblocks_ = 0;
     float* cloud_ = nullptr;               // device copy of the host cloud
     float* pinned_cloud_ = nullptr;
+    cudaEvent_t cloud_uploaded_ = nullptr;   // the pinned staging buffer may be rewritten once this has fired
     unsigned long long* packed_ = nullptr; // (point index + 1) << 32 | depth bits : last writer wins
     float *bg_ = nullptr, *diff_ = nullptr, *ring_ = nullptr;
     int* label_img_ = nullptr;
