@@ -59,12 +59,17 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // 128 tensor cycles: one producer thread cannot feed the tensor core, four can.  Producer and issuer
 // loops run warp-converged (one elected lane issues) so the bookkeeping stays in the uniform datapath;
 // two CTAs per SM let one CTA's epilogue hide behind the other's main loop.
-template <int kMode>   // 0: one TMA box per filter tap; 1: same + split-K; 2: halo tile (3x3 stride 1)
+template <int kMode>   // 0: one TMA box per filter tap; 1: + split-K; 2: halo tile (3x3 stride 1); 3: CTA pair (cta_group::2)
 __global__ void __launch_bounds__(kThreads, 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ ConvParams p) {
     constexpr bool kSplit = (kMode == 1);
     constexpr bool kHalo = (kMode == 2);
+    constexpr bool kPair = (kMode == 3);
+    // CTA pair: two M-tiles (blockIdx.x even / odd) share one MMA stream issued by the even (leader) CTA:
+    // one tcgen05.mma covers 256 x N, each CTA stages its own activation tile and half of the weight tile
+    const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+    const bool is_leader = cta_rank == 0u;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[kMaxStages];
     __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
@@ -112,8 +117,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
-        tmem_relinquish();
+        if (kPair) {
+            tmem_alloc_2sm(smem_u32(&tmem_base_slot), p.tmem_cols);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
+            tmem_relinquish();
+        }
     } else {
         if (static_cast<int>(threadIdx.x) < p.block_n) s_bias[threadIdx.x] = __ldg(p.bias + ch0 + threadIdx.x);
     }
@@ -121,6 +131,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    if (kPair) cluster_sync_all();   // the peer's barriers exist before anything signals them
     pdl_launch_dependents();
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
@@ -140,8 +151,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (it >= p.stages) mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
                 if (leader) {
                     if (dbg && it < 10) dbg[54 + it] = clock64();
-                    tma_load_2d(smem_base + stage * p.stage_stride + p.b_off, &tm_b, smem_u32(&bar_full[stage]),
-                                (it0 + it) * p.bk, ch0);
+                    if (kPair)   // this CTA's half of the weight rows; completion is counted on the leader's barrier
+                        tma_load_2d_2sm(smem_base + stage * p.stage_stride + p.b_off, &tm_b, smem_u32(&bar_full[stage]),
+                                        (it0 + it) * p.bk, ch0 + static_cast<int>(cta_rank) * (p.block_n >> 1));
+                    else
+                        tma_load_2d(smem_base + stage * p.stage_stride + p.b_off, &tm_b, smem_u32(&bar_full[stage]),
+                                    (it0 + it) * p.bk, ch0);
                 }
                 __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -173,7 +188,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int ksteps = p.bk >> 4;
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = 0; it < num_it; ++it) {
+            for (int it = 0; it < (is_leader ? num_it : 0); ++it) {
                 if (dbg && leader && it < 10) dbg[44 + it] = clock64();
                 mbar_wait(smem_u32(&bar_full[stage]), phase);
                 tc_fence_after();
@@ -183,9 +198,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * stage_step);
                     // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
                     const int kmax = (p.dbg_flags & 1) ? 0 : ((p.dbg_flags & 2) ? 1 : ksteps);
-                    for (int k = 0; k < kmax; ++k)
-                        umma_f16(tmem_base, ad + 2u * k, bd + 2u * k, p.idesc, (it | k) != 0);
-                    umma_commit(smem_u32(&bar_empty[stage]));   // frees the smem slot when the MMAs retire
+                    for (int k = 0; k < kmax; ++k) {
+                        if (kPair) umma_f16_2sm(tmem_base, ad + 2u * k, bd + 2u * k, p.idesc, (it | k) != 0);
+                        else umma_f16(tmem_base, ad + 2u * k, bd + 2u * k, p.idesc, (it | k) != 0);
+                    }
+                    // frees the smem slot (in both CTAs of a pair) when the MMAs retire
+                    if (kPair) umma_commit_2sm(smem_u32(&bar_empty[stage]), 3);
+                    else umma_commit(smem_u32(&bar_empty[stage]));
                 }
                 __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -225,8 +244,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
             }
         }
-        if (leader) {
-            umma_commit(smem_u32(&bar_acc));                // accumulator complete
+        if (leader && is_leader) {
+            if (kPair) umma_commit_2sm(smem_u32(&bar_acc), 3);   // accumulator complete (both halves)
+            else umma_commit(smem_u32(&bar_acc));
             if (dbg) dbg[18] = clock64();
         }
         __syncwarp();
@@ -262,10 +282,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const uint32_t full = smem_u32(&bar_full[stage]);
                     if (it >= p.stages) mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
                     if (leader) {
-                        mbar_expect_tx(full, tx);
+                        // a pair's bytes (two activation tiles + two weight halves) are all counted on the
+                        // leader's barrier, which only the leader arms
+                        if (is_leader) mbar_expect_tx(full, kPair ? 2u * tx : tx);
                         if (dbg && it < 16) dbg[24 + it] = clock64();
-                        tma_load_5d(smem_base + stage * p.stage_stride, &tm_a, full,
-                                    p.cin_coff + t.x + kc * p.bk, ow0 + t.y, t.z, oh0 + t.w, n0);
+                        if (kPair)
+                            tma_load_5d_2sm(smem_base + stage * p.stage_stride, &tm_a, full,
+                                            p.cin_coff + t.x + kc * p.bk, ow0 + t.y, t.z, oh0 + t.w, n0);
+                        else
+                            tma_load_5d(smem_base + stage * p.stage_stride, &tm_a, full,
+                                        p.cin_coff + t.x + kc * p.bk, ow0 + t.y, t.z, oh0 + t.w, n0);
                     }
                     __syncwarp();
                 }
@@ -458,9 +484,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (dbg && threadIdx.x == 0) dbg[21] = clock64();
+    if (kPair) cluster_sync_all();   // both CTAs are done with each other's barriers and tensor memory
     if (warp == 4) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, p.tmem_cols);
+        if (kPair) tmem_dealloc_2sm(tmem_base, p.tmem_cols);
+        else tmem_dealloc(tmem_base, p.tmem_cols);
     }
 }
 
@@ -738,6 +766,18 @@ bool split_k_enabled() {
 // bytes of 3x3 layers 4x, yet the main loop is bound by the single-thread MMA issue sequence
 // (~135 cycles barrier wait + ~240 commit/loop + ~85 per UTCHMMA, measured with RMR_DBG_FLAGS), not by
 // operand bytes, so the replay time does not move (car 0.448 vs 0.435 ms).  RMR_HALO=1 turns it on.
+// CTA pairs (cta_group::2, cluster of two M-tiles, one MMA stream for 256 x N) are parity-green but OFF by
+// default: measured on B200 a pair's k-block period is ~600 cycles for two tiles, the same per-SM rate two
+// independent CTAs on one SM already reach (2 x ~575 concurrently), and the cluster syncs add ~1300 cycles
+// of setup — graph replay car 0.529 vs 0.477 ms, armor(7) 1.110 vs 0.982 ms.  RMR_PAIR=1 turns it on.
+bool pair_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("RMR_PAIR");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
 bool halo_enabled() {
     static const bool on = [] {
         const char* e = std::getenv("RMR_HALO");
@@ -805,8 +845,9 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
     p.tiles_n = (d.n + p.tn - 1) / p.tn;
     p.block_n = pick_block_n(d.cout_pad, static_cast<long>(p.tiles_w) * p.tiles_h * p.tiles_n);
     // operand ring: A = 128 pixel rows x BK, B = block_n rows x BK (both multiples of 1 KB)
+    p.pair = (pair_enabled() && !p.halo && p.tiles_w * p.tiles_h * p.tiles_n >= 2) ? 1 : 0;
     p.a_bytes = 128u * p.bk * 2u;
-    p.b_bytes = static_cast<uint32_t>(p.block_n) * p.bk * 2u;
+    p.b_bytes = static_cast<uint32_t>(p.pair ? p.block_n / 2 : p.block_n) * p.bk * 2u;
     p.b_off = p.a_bytes;
     p.stage_stride = p.a_bytes + p.b_bytes;
     p.stages = std::max(1, std::min({kMaxStages, static_cast<int>(kSmemBudget / p.stage_stride), p.ntaps * p.kpt}));
@@ -828,7 +869,7 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
         const long ctas = static_cast<long>(p.tiles_w) * p.tiles_h * p.tiles_n * (d.cout_pad / p.block_n);
         const int num_it = p.ntaps * p.kpt;
         int splits = 1;
-        if (split_k_enabled() && !p.halo && ctas * 3 <= 148 && num_it >= 16) {
+        if (split_k_enabled() && !p.halo && !p.pair && ctas * 3 <= 148 && num_it >= 16) {
             const int want = static_cast<int>(std::min<long>(16, 148 / ctas));
             const int ips = std::max(4, (num_it + want - 1) / want);
             splits = (num_it + ips - 1) / ips;
@@ -856,7 +897,8 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
     p.res = d.res; p.res_pitch = d.res_pitch; p.res_coff = d.res_coff;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A/B=f16 (0), K-major both,
     // N>>3 at [17,23), M>>4 at [24,29)
-    p.idesc = (1u << 4) | (static_cast<uint32_t>(p.block_n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+    p.idesc = (1u << 4) | (static_cast<uint32_t>(p.block_n >> 3) << 17) |
+              (static_cast<uint32_t>((p.pair ? 256 : 128) >> 4) << 24);
     p.sbo = (p.bk == 64) ? 1024u : 512u;
     p.layout = (p.bk == 64) ? 2u : 4u;
     const CUtensorMapSwizzle swz = (p.bk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -884,10 +926,11 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
         const cuuint64_t ktot = static_cast<cuuint64_t>(p.ntaps) * d.cin_pad;
         cuuint64_t dims[2] = {ktot, static_cast<cuuint64_t>(d.cout_pad)};
         cuuint64_t strides[1] = {ktot * 2};
-        cuuint32_t box[2] = {static_cast<cuuint32_t>(p.bk), static_cast<cuuint32_t>(p.block_n)};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(p.bk), static_cast<cuuint32_t>(p.pair ? p.block_n / 2 : p.block_n)};
         encode(&l.tm_b, const_cast<__half*>(d.w), 2, dims, strides, box, swz);
     }
     l.grid = dim3(p.tiles_w * p.tiles_h * p.tiles_n, d.cout_pad / p.block_n, p.splits);
+    if (p.pair) l.grid.x = (l.grid.x + 1) / 2 * 2;   // clusters of two M-tiles; a padding tile is all out of range
     l.smem_bytes = smem_total + 1024;
     l.flops = 2.0 * d.n * d.h_out * d.w_out * static_cast<double>(d.cout) * d.k * d.k * d.cin;
     return l;
@@ -922,6 +965,10 @@ void conv_init() {
                                       kSmemBudget + 1024));
         RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       cudaSharedmemCarveoutMaxShared));
+        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kSmemBudget + 1024));
+        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
         RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       2 * kSmemBudget + 1024));
         RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -939,12 +986,24 @@ void launch_conv_umma(const ConvLaunch& l, cudaStream_t s, bool pdl) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = static_cast<size_t>(l.smem_bytes);
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (g_use_pdl && pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (l.p.pair) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = (g_use_pdl && pdl) ? 1 : 0;
-    if (l.p.halo) RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2>, l.tm_a, l.tm_b, l.p));
+    cfg.numAttrs = na;
+    if (l.p.pair) RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<3>, l.tm_a, l.tm_b, l.p));
+    else if (l.p.halo) RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2>, l.tm_a, l.tm_b, l.p));
     else if (l.p.splits > 1) RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1>, l.tm_a, l.tm_b, l.p));
     else RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<0>, l.tm_a, l.tm_b, l.p));
 }

@@ -1,4 +1,4 @@
-"""GPU: the optional conv operand modes (halo-tile A operand, split-K) against the CUDA-core direct conv.
+"""GPU: the optional conv modes (halo-tile A operand, split-K, CTA pairs) against the CUDA-core direct conv.
 Both are selected by environment variables read once per process, so each mode runs in a subprocess."""
 import json
 import os
@@ -27,8 +27,14 @@ SPLIT_SHAPES = [(1, 20, 20, 512, 64, 3, 1, 1, 0, 0), (1, 20, 20, 256, 256, 3, 1,
                 (1, 20, 20, 1024, 512, 1, 1, 1, 0, 0), (1, 40, 40, 256, 256, 3, 2, 1, 0, 0)]
 
 
-@pytest.mark.parametrize("env,shapes", [({"RMR_HALO": "1"}, HALO_SHAPES), ({"RMR_SPLITK": "1"}, SPLIT_SHAPES)],
-                         ids=["halo", "split_k"])
+PAIR_SHAPES = [(1, 160, 160, 64, 64, 3, 1, 1, 0, 0), (1, 320, 320, 32, 64, 3, 2, 1, 0, 0), (3, 80, 80, 128, 12, 1, 1, 0, 0, 1),
+               (8, 10, 10, 512, 512, 3, 1, 1, 1, 0), (1, 20, 20, 256, 256, 3, 1, 1, 1, 0), (5, 20, 20, 384, 384, 3, 2, 1, 0, 0),
+               (1, 40, 40, 768, 256, 1, 1, 1, 0, 0)]
+
+
+@pytest.mark.parametrize("env,shapes", [({"RMR_HALO": "1"}, HALO_SHAPES), ({"RMR_SPLITK": "1"}, SPLIT_SHAPES),
+                                        ({"RMR_PAIR": "1"}, PAIR_SHAPES)],
+                         ids=["halo", "split_k", "cta_pair"])
 def test_optional_conv_modes_match_direct(env, shapes):
     e = dict(os.environ, **env)
     e["PYTHONPATH"] = fx.ROOT + os.pathsep + e.get("PYTHONPATH", "")
