@@ -387,6 +387,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                             for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(f[8 * j + 2 * u], f[8 * j + 2 * u + 1]);
                             reinterpret_cast<uint4*>(o)[j] = w;
+                            if (p.dup_mode == 1) {
+                                reinterpret_cast<uint4*>(p.dup + pix * p.dup_pitch + p.dup_coff + ch0 + c0)[j] = w;
+                            } else if (p.dup_mode == 2) {
+                                // nearest 2x upsample written by the producer: (oh, ow) -> (2oh + dy, 2ow + dx)
+                                const size_t up = (static_cast<size_t>(n) * (2 * p.h_out) + 2 * oh) * (2 * p.w_out) + 2 * ow;
+                                __half* u0 = p.dup + up * p.dup_pitch + p.dup_coff + ch0 + c0;
+                                __half* u1 = u0 + static_cast<size_t>(2 * p.w_out) * p.dup_pitch;
+                                reinterpret_cast<uint4*>(u0)[j] = w;
+                                reinterpret_cast<uint4*>(u0 + p.dup_pitch)[j] = w;
+                                reinterpret_cast<uint4*>(u1)[j] = w;
+                                reinterpret_cast<uint4*>(u1 + p.dup_pitch)[j] = w;
+                            }
                         }
                     }
                 } else {
@@ -895,6 +907,7 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
     p.out = d.out; p.out_pitch = d.out_pitch; p.out_coff = d.out_coff; p.out_f32 = d.out_f32;
     p.bias = d.bias; p.act = d.act;
     p.res = d.res; p.res_pitch = d.res_pitch; p.res_coff = d.res_coff;
+    p.dup = d.dup; p.dup_pitch = d.dup_pitch; p.dup_coff = d.dup_coff; p.dup_mode = d.dup_mode;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A/B=f16 (0), K-major both,
     // N>>3 at [17,23), M>>4 at [24,29)
     p.idesc = (1u << 4) | (static_cast<uint32_t>(p.block_n >> 3) << 17) |

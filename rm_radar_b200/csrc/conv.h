@@ -13,6 +13,10 @@ struct ConvDesc {
     int k = 1, stride = 1, act = 0;
     const __half* res = nullptr;
     int res_pitch = 0, res_coff = 0;
+    // optional second destination of the same fp16 result: a plain copy (dup_mode 1: Concat input with two
+    // homes) or a nearest-neighbour 2x upsample (dup_mode 2: each pixel lands on its 2x2 block)
+    __half* dup = nullptr;
+    int dup_pitch = 0, dup_coff = 0, dup_mode = 0;
     const __half* w = nullptr;   // [cout_pad][k*k][cin_pad] fp16
     const float* bias = nullptr; // [cout_pad]
     int cout_pad = 0, cin_pad = 0;
@@ -31,6 +35,8 @@ struct ConvParams {
     int act;
     const __half* res;
     int res_pitch, res_coff;
+    __half* dup;
+    int dup_pitch, dup_coff, dup_mode;
     uint32_t idesc, sbo, layout;
     uint32_t a_bytes, b_bytes, b_off, stage_stride, tmem_cols;   // operand ring geometry
     int stages, vec_ok;

@@ -113,6 +113,30 @@ Net::BatchPlan& Net::plan_for(int batch) {
         }
         bp.steps.push_back(st);
     }
+    // Upsample / Concat-copy of a conv result -> second destination of that conv's epilogue (no launch)
+    for (size_t j = 0; j < bp.steps.size() && !force_simt_; ++j) {
+        const EngineOp& u = bp.steps[j].op;
+        if (bp.steps[j].type != OP_UPSAMPLE2 && bp.steps[j].type != OP_COPY) continue;
+        for (size_t i = j; i-- > 0;) {
+            Step& c = bp.steps[i];
+            const EngineOp& co = c.op;
+            const bool writes_src = co.dst_buf == u.src_buf && co.dst_coff < u.src_coff + u.src_c &&
+                                    u.src_coff < co.dst_coff + (co.type == OP_CONV ? co.dst_c : co.src_c);
+            if (!writes_src) continue;
+            const bool exact = c.type == OP_CONV && c.umma && co.dst_coff == u.src_coff && co.dst_c == u.src_c &&
+                               buf_desc_[co.dst_buf].dtype == 0 && c.desc.dup == nullptr && (co.dst_c % 8) == 0 &&
+                               (buf_desc_[u.dst_buf].c % 8) == 0 && (u.dst_coff % 8) == 0 && c.launch.p.vec_ok;
+            if (exact) {
+                c.desc.dup = static_cast<__half*>(bufs_[u.dst_buf]);
+                c.desc.dup_pitch = buf_desc_[u.dst_buf].c;
+                c.desc.dup_coff = u.dst_coff;
+                c.desc.dup_mode = bp.steps[j].type == OP_UPSAMPLE2 ? 2 : 1;
+                c.launch = make_conv_launch(c.desc);
+                bp.steps[j].type = OP_FUSED_AWAY;
+            }
+            break;   // the most recent writer of the source decides
+        }
+    }
     // split-K scratch: every split layer gets its own region (layers on different graph lanes overlap)
     size_t scratch = 0;
     for (const Step& st : bp.steps)
