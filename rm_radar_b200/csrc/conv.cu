@@ -27,8 +27,10 @@ namespace rmr {
 namespace {
 
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 320;
+constexpr int kThreads = 320;        // wide variant: 4 producer/epilogue + MMA + weight producer + 4 epilogue-only warps
+constexpr int kThreadsSlim = 192;    // slim variant: no epilogue-only warps, three CTAs per SM
 constexpr int kSmemBudget = 100 * 1024;   // operand ring per CTA: two CTAs co-reside on one SM
+constexpr int kSmemBudgetSlim = 72 * 1024;   // slim variant: three CTAs per SM
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -59,8 +61,11 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // 128 tensor cycles: one producer thread cannot feed the tensor core, four can.  Producer and issuer
 // loops run warp-converged (one elected lane issues) so the bookkeeping stays in the uniform datapath;
 // two CTAs per SM let one CTA's epilogue hide behind the other's main loop.
-template <int kMode>   // 0: one TMA box per filter tap; 1: + split-K; 2: halo tile (3x3 stride 1); 3: CTA pair (cta_group::2)
-__global__ void __launch_bounds__(kThreads, 2)
+// kMode 0: one TMA box per filter tap; 1: + split-K; 2: halo tile (3x3 stride 1); 3: CTA pair (cta_group::2).
+// kSlim: 192 threads and three CTAs per SM instead of 320 threads and two — for N <= 64 layers with many
+// tiles, where what limits an SM is the number of concurrent MMA issue streams, not the epilogue.
+template <int kMode, bool kSlim = false>
+__global__ void __launch_bounds__(kSlim ? kThreadsSlim : kThreads, kSlim ? 3 : 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ ConvParams p) {
     constexpr bool kSplit = (kMode == 1);
@@ -303,6 +308,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // the two warps of a quarter interleave 32-column chunks (0, 64, .. / 32, 96, ..)
         const int q = warp & 3;
         const int chunk0 = warp >= 6 ? 32 : 0;
+        constexpr int kChunkStep = kSlim ? 32 : 64;   // slim: one warp per lane quarter takes every chunk
         const int row = q * 32 + lane;
         const int tw_i = row % p.tw;
         const int th_i = (row / p.tw) % p.th;
@@ -415,14 +421,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             mbar_wait(smem_u32(&bar_acc), 0);
             if (dbg && threadIdx.x == 0) dbg[19] = clock64();
             tc_fence_after();
-            for (int c0 = chunk0; c0 < nvalid; c0 += 64) {
+            for (int c0 = chunk0; c0 < nvalid; c0 += kChunkStep) {
                 uint32_t v[32];
                 __syncwarp();   // tcgen05.ld is warp-aligned: reconverge after the predicated stores
                 tmem_ld_32(taddr + c0, v);
                 uint4 rcur[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-                if (c0 + 64 < nvalid) fetch_res(c0 + 64);
+                if (c0 + kChunkStep < nvalid) fetch_res(c0 + kChunkStep);
                 tmem_ld_wait();
                 if (dbg && threadIdx.x == 0 && c0 == chunk0) dbg[40] = clock64();
                 if (valid) {
@@ -442,7 +448,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             mbar_wait(smem_u32(&bar_acc), 0);
             if (dbg && threadIdx.x == 0) dbg[19] = clock64();
             tc_fence_after();
-            for (int c0 = chunk0; c0 < nvalid; c0 += 64) {
+            for (int c0 = chunk0; c0 < nvalid; c0 += kChunkStep) {
                 uint32_t v[32];
                 __syncwarp();
                 tmem_ld_32(taddr + c0, v);
@@ -456,21 +462,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
             }
             if (dbg && threadIdx.x == 0) dbg[43] = clock64();
-            asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps: all partial stores issued
+            asm volatile("bar.sync 1, %0;" ::"n"(kSlim ? 128 : 256) : "memory");   // the epilogue warps: all partial stores issued
             if (threadIdx.x == 0) {
                 __threadfence();   // cumulative: publishes the CTA's stores ordered before it by the barrier
                 s_last = (atomicAdd(p.counters + tile_lin, 1) == p.splits - 1) ? 1 : 0;
                 __threadfence();
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kSlim ? 128 : 256) : "memory");
             if (dbg && threadIdx.x == 0) dbg[44] = clock64();
             if (s_last) {
                 fetch_res(chunk0);
-                for (int c0 = chunk0; c0 < nvalid; c0 += 64) {
+                for (int c0 = chunk0; c0 < nvalid; c0 += kChunkStep) {
                     uint4 rcur[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-                    if (c0 + 64 < nvalid) fetch_res(c0 + 64);
+                    if (c0 + kChunkStep < nvalid) fetch_res(c0 + kChunkStep);
                     if (valid) {
                         float f[32];
 #pragma unroll
@@ -790,6 +796,14 @@ bool pair_enabled() {
     return on;
 }
 
+bool slim_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("RMR_NO_SLIM");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
+
 bool halo_enabled() {
     static const bool on = [] {
         const char* e = std::getenv("RMR_HALO");
@@ -891,6 +905,12 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
         p.splits = splits;
         p.stages = std::max(1, std::min(p.stages, p.it_per_split));
         p.part_ld = (p.block_n + 31) / 32 * 32;
+        // slim variant: N <= 64 and more CTAs than two full waves of the wide variant
+        p.slim = (slim_enabled() && !p.halo && !p.pair && splits == 1 && p.block_n <= 64 && ctas > 2 * 148) ? 1 : 0;
+        if (p.slim) {
+            p.stages = std::max(1, std::min({kMaxStages, static_cast<int>(kSmemBudgetSlim / p.stage_stride), num_it}));
+            smem_total = p.stages * static_cast<int>(p.stage_stride);
+        }
     }
     const int out_align = d.out_f32 ? 4 : 8;
     p.vec_ok = (d.out_pitch % out_align == 0 && d.out_coff % out_align == 0 &&
@@ -978,6 +998,10 @@ void conv_init() {
                                       kSmemBudget + 1024));
         RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       cudaSharedmemCarveoutMaxShared));
+        RMR_CUDA((cudaFuncSetAttribute(conv_umma_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kSmemBudgetSlim + 1024)));
+        RMR_CUDA((cudaFuncSetAttribute(conv_umma_kernel<0, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared)));
         RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kSmemBudget + 1024));
         RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -996,7 +1020,7 @@ void launch_conv_umma(const ConvLaunch& l, cudaStream_t s, bool pdl) {
     conv_init();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = l.grid;
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(l.p.slim ? kThreadsSlim : kThreads);
     cfg.dynamicSmemBytes = static_cast<size_t>(l.smem_bytes);
     cfg.stream = s;
     cudaLaunchAttribute attr[2];
@@ -1015,7 +1039,8 @@ void launch_conv_umma(const ConvLaunch& l, cudaStream_t s, bool pdl) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    if (l.p.pair) RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<3>, l.tm_a, l.tm_b, l.p));
+    if (l.p.slim) RMR_CUDA((cudaLaunchKernelEx(&cfg, conv_umma_kernel<0, true>, l.tm_a, l.tm_b, l.p)));
+    else if (l.p.pair) RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<3>, l.tm_a, l.tm_b, l.p));
     else if (l.p.halo) RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2>, l.tm_a, l.tm_b, l.p));
     else if (l.p.splits > 1) RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1>, l.tm_a, l.tm_b, l.p));
     else RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<0>, l.tm_a, l.tm_b, l.p));

@@ -8,9 +8,18 @@ tests.  Record layout (8 float32 per robot, `max_cars` rows per rank):
 """
 from __future__ import annotations
 
+import ctypes
+
+import numpy as np
 import torch
 
 RECORD_FLOATS = 8
+
+# numpy view of include/rm_radar_b200.h `rmr_robot_t` (same layout as _lib.RobotRec)
+ROBOT_DTYPE = np.dtype([("rect", np.float32, 4), ("has_rect", np.int32), ("is_detected", np.int32), ("label", np.int32),
+                        ("confidence", np.float32), ("n_armors", np.int32), ("armors", np.float32, (16, 6)),
+                        ("is_located", np.int32), ("location", np.float32, 3), ("cluster", np.int32),
+                        ("cluster_points", np.int32)])
 
 
 def pack_records(recs, n: int, max_cars: int, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -19,7 +28,19 @@ def pack_records(recs, n: int, max_cars: int, out: torch.Tensor | None = None) -
         out = torch.zeros(max_cars, RECORD_FLOATS)
     else:
         out.zero_()
-    for i in range(min(n, max_cars)):
+    n = min(n, max_cars)
+    if isinstance(recs, ctypes.Array) and ctypes.sizeof(recs._type_) == ROBOT_DTYPE.itemsize:
+        # the C ABI's record array: one vectorised pass, no per-robot Python work
+        a = np.frombuffer(recs, dtype=ROBOT_DTYPE, count=n)
+        o = out.numpy()
+        o[:n, 0] = 1.0
+        o[:n, 1] = np.where(a["is_detected"] != 0, a["label"], -1)
+        o[:n, 2] = a["confidence"]
+        o[:n, 3] = a["is_located"] != 0
+        o[:n, 4:7] = a["location"] * (a["is_located"] != 0)[:, None]
+        o[:n, 7] = a["rect"][:, 2] * a["rect"][:, 3]
+        return out
+    for i in range(n):
         r = recs[i]
         out[i, 0] = 1.0
         out[i, 1] = float(r.label) if r.is_detected else -1.0

@@ -56,3 +56,21 @@ def test_all_gather_of_robot_records_world2():
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mp.spawn(worker, args=(2, port), nprocs=2, join=True)
+
+
+def test_pack_records_fast_path_matches_generic():
+    """The vectorised view of the C ABI's rmr_robot_t array and the generic per-robot path agree."""
+    import ctypes
+    from rm_radar_b200 import _lib
+    assert ctypes.sizeof(_lib.RobotRec) == rdist.ROBOT_DTYPE.itemsize
+    recs = (_lib.RobotRec * MAX_CARS)()
+    for i in range(6):
+        recs[i].label = i
+        recs[i].is_detected = int(i != 2)
+        recs[i].confidence = 0.5 + 0.1 * i
+        recs[i].is_located = i % 2
+        recs[i].location = (ctypes.c_float * 3)(1.0 + i, 2.0, 3.0)
+        recs[i].rect = (ctypes.c_float * 4)(1, 2, 3 + i, 4)
+    fast = rdist.pack_records(recs, 6, MAX_CARS)
+    slow = rdist.pack_records([recs[i] for i in range(6)], 6, MAX_CARS)
+    assert torch.equal(fast, slow)
