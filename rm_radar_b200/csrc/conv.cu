@@ -64,7 +64,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // kMode 0: one TMA box per filter tap; 1: + split-K; 2: halo tile (3x3 stride 1); 3: CTA pair (cta_group::2).
 // kSlim: 192 threads and three CTAs per SM instead of 320 threads and two — for N <= 64 layers with many
 // tiles, where what limits an SM is the number of concurrent MMA issue streams, not the epilogue.
-template <int kMode, bool kSlim = false>
+template <int kMode, bool kSlim = false, bool kRes = true>   // kRes: the layer has a shortcut operand
 __global__ void __launch_bounds__(kSlim ? kThreadsSlim : kThreads, kSlim ? 3 : 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ ConvParams p) {
@@ -113,7 +113,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 mbar_init(smem_u32(&bar_full[i]), 1);
                 mbar_init(smem_u32(&bar_empty[i]), 1);
             }
-            mbar_init(smem_u32(&bar_acc), 1);
+            mbar_init(smem_u32(&bar_acc), p.dual ? 2 : 1);
             if (kHalo)
                 for (int i = 0; i < 2; ++i) {
                     mbar_init(smem_u32(&bar_afull[i]), 1);
@@ -143,6 +143,52 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // split-K: blockIdx.z owns k-blocks [it0, it0 + num_it) of the taps x channel-chunks sequence
     const int it0 = kSplit ? blockIdx.z * p.it_per_split : 0;
     const int num_it = kSplit ? min(p.it_per_split, p.ntaps * p.kpt - it0) : p.ntaps * p.kpt;
+
+    // One MMA issue stream: k-blocks first, first + step, ... accumulate into TMEM columns [acc, acc + N).
+    // With step 2 two warps (4 and 6) each drive half of the k-blocks into their own accumulator and the
+    // epilogue adds the two: what bounds a lone CTA is the ~575-cycle issue sequence per k-block
+    // (barrier wait + 4 x tcgen05.mma + commit), and two sequences overlap.  The ring has an even number
+    // of slots in that case, so a slot always belongs to the same stream (a parity wait cannot tell phases
+    // two apart).
+    auto mma_stream = [&](int first, int step, uint32_t acc) {
+        const bool leader = elect_one();
+        const uint64_t adesc0 = umma_smem_desc(smem_base, p.sbo, p.layout);
+        const uint64_t bdesc0 = umma_smem_desc(smem_base + p.b_off, p.sbo, p.layout);
+        const uint32_t stage_step = p.stage_stride >> 4;   // descriptor start-address units (16 B)
+        const int ksteps = p.bk >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < (is_leader ? num_it : 0); ++it) {
+            if (it >= first && ((it - first) & (step - 1)) == 0) {
+                if (dbg && leader && first == 0 && it < 10) dbg[44 + it] = clock64();
+                mbar_wait(smem_u32(&bar_full[stage]), phase);
+                tc_fence_after();
+                if (leader) {
+                    if (dbg && it < 16) dbg[2 + it] = clock64();
+                    const uint64_t ad = adesc0 + static_cast<uint64_t>(stage * stage_step);
+                    const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * stage_step);
+                    // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+                    const int kmax = (p.dbg_flags & 1) ? 0 : ((p.dbg_flags & 2) ? 1 : ksteps);
+                    for (int k = 0; k < kmax; ++k) {
+                        const uint32_t accumulate = (it != first || k != 0) ? 1u : 0u;
+                        if (kPair) umma_f16_2sm(tmem_base + acc, ad + 2u * k, bd + 2u * k, p.idesc, accumulate);
+                        else umma_f16(tmem_base + acc, ad + 2u * k, bd + 2u * k, p.idesc, accumulate);
+                    }
+                    // frees the smem slot (in both CTAs of a pair) when the MMAs retire
+                    if (kPair) umma_commit_2sm(smem_u32(&bar_empty[stage]), 3);
+                    else umma_commit(smem_u32(&bar_empty[stage]));
+                }
+                __syncwarp();
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (leader && is_leader) {
+            if (kPair) umma_commit_2sm(smem_u32(&bar_acc), 3);   // accumulator complete (both halves of a pair)
+            else umma_commit(smem_u32(&bar_acc));
+            if (dbg && first == 0) dbg[18] = clock64();
+        }
+        __syncwarp();
+    };
 
     if (warp == 5) {
         // ------------------------------ B (weight) producer ------------------------------
@@ -187,33 +233,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // ------------------------------ MMA issuer ------------------------------
         const bool leader = elect_one();
         if (!kHalo) {
-            const uint64_t adesc0 = umma_smem_desc(smem_base, p.sbo, p.layout);
-            const uint64_t bdesc0 = umma_smem_desc(smem_base + p.b_off, p.sbo, p.layout);
-            const uint32_t stage_step = p.stage_stride >> 4;   // descriptor start-address units (16 B)
-            const int ksteps = p.bk >> 4;
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int it = 0; it < (is_leader ? num_it : 0); ++it) {
-                if (dbg && leader && it < 10) dbg[44 + it] = clock64();
-                mbar_wait(smem_u32(&bar_full[stage]), phase);
-                tc_fence_after();
-                if (leader) {
-                    if (dbg && it < 16) dbg[2 + it] = clock64();
-                    const uint64_t ad = adesc0 + static_cast<uint64_t>(stage * stage_step);
-                    const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * stage_step);
-                    // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
-                    const int kmax = (p.dbg_flags & 1) ? 0 : ((p.dbg_flags & 2) ? 1 : ksteps);
-                    for (int k = 0; k < kmax; ++k) {
-                        if (kPair) umma_f16_2sm(tmem_base, ad + 2u * k, bd + 2u * k, p.idesc, (it | k) != 0);
-                        else umma_f16(tmem_base, ad + 2u * k, bd + 2u * k, p.idesc, (it | k) != 0);
-                    }
-                    // frees the smem slot (in both CTAs of a pair) when the MMAs retire
-                    if (kPair) umma_commit_2sm(smem_u32(&bar_empty[stage]), 3);
-                    else umma_commit(smem_u32(&bar_empty[stage]));
-                }
-                __syncwarp();
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-            }
+            mma_stream(0, p.dual ? 2 : 1, 0u);
         } else {
             // Halo mode.  The activation patch of one 64-channel chunk is [18 rows][16 cols] pixels x 128 B
             // (SWIZZLE_128B as written by TMA, slot base 1024-aligned).  The A operand of tap (dy, dx) is the
@@ -249,9 +269,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
             }
         }
-        if (leader && is_leader) {
-            if (kPair) umma_commit_2sm(smem_u32(&bar_acc), 3);   // accumulator complete (both halves)
-            else umma_commit(smem_u32(&bar_acc));
+        if (kHalo && leader) {
+            umma_commit(smem_u32(&bar_acc));   // accumulator complete
             if (dbg) dbg[18] = clock64();
         }
         __syncwarp();
@@ -304,6 +323,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
         }
+        if (!kSlim && !kHalo && warp == 6 && p.dual) mma_stream(1, 2, p.acc_stride);   // second issue stream
         // ---------------- epilogue: warps 0-3 and 6-9; TMEM lane quarter = warp % 4 ----------------
         // the two warps of a quarter interleave 32-column chunks (0, 64, .. / 32, 96, ..)
         const int q = warp & 3;
@@ -317,13 +337,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const bool valid = (ow < p.w_out) && (oh < p.h_out) && (n < p.n);
         const size_t pix = (static_cast<size_t>(n) * p.h_out + oh) * p.w_out + ow;
         const int nvalid = min(p.block_n, p.cout - ch0);   // real output channels in this tile
-        const __half* rptr = (p.res != nullptr && valid) ? p.res + pix * p.res_pitch + p.res_coff + ch0 : nullptr;
+        const __half* rptr = (kRes && p.res != nullptr && valid) ? p.res + pix * p.res_pitch + p.res_coff + ch0 : nullptr;
         const bool vec = p.vec_ok != 0;
 
         uint4 rnext[4];
         auto fetch_res = [&](int c0) {
             const int cnt = nvalid - c0;
-            if (rptr != nullptr && vec && cnt >= 16) {
+            if (kRes && rptr != nullptr && vec && cnt >= 16) {
                 rnext[0] = *reinterpret_cast<const uint4*>(rptr + c0);
                 rnext[1] = *reinterpret_cast<const uint4*>(rptr + c0 + 8);
                 if (cnt >= 32) {
@@ -338,14 +358,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += s_bias[c0 + j];
             if (p.act) {
-                // SiLU, staged so that the 32 independent MUFU chains pipeline (ex2 pass, then rcp pass)
-                float e[32];
+                // SiLU, staged so that 16 independent MUFU chains pipeline (ex2 pass, then rcp pass) without
+                // doubling the live registers of the whole chunk
 #pragma unroll
-                for (int j = 0; j < 32; ++j) e[j] = 1.0f + exp2f_approx(-1.4426950408889634f * f[j]);
+                for (int h0 = 0; h0 < 32; h0 += 16) {
+                    float e[16];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = f[j] * rcp_approx(e[j]);
+                    for (int j = 0; j < 16; ++j) e[j] = 1.0f + exp2f_approx(-1.4426950408889634f * f[h0 + j]);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[h0 + j] = f[h0 + j] * rcp_approx(e[j]);
+                }
             }
-            if (rptr != nullptr) {
+            if (kRes && rptr != nullptr) {
                 if (vec && cnt >= 16) {
                     const __half2* h = reinterpret_cast<const __half2*>(rcur);
 #pragma unroll
@@ -417,7 +441,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         if (!kSplit) {
-            fetch_res(chunk0);
             mbar_wait(smem_u32(&bar_acc), 0);
             if (dbg && threadIdx.x == 0) dbg[19] = clock64();
             tc_fence_after();
@@ -425,18 +448,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 uint32_t v[32];
                 __syncwarp();   // tcgen05.ld is warp-aligned: reconverge after the predicated stores
                 tmem_ld_32(taddr + c0, v);
-                uint4 rcur[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-                if (c0 + kChunkStep < nvalid) fetch_res(c0 + kChunkStep);
+                fetch_res(c0);   // shortcut operand of this chunk: in flight while the accumulator is read
                 tmem_ld_wait();
                 if (dbg && threadIdx.x == 0 && c0 == chunk0) dbg[40] = clock64();
-                if (valid) {
-                    float f[32];
+                float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    finish_chunk(c0, f, rcur);
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.dual) {   // the second issue stream's accumulator
+                    tmem_ld_32(taddr + p.acc_stride + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
                 }
+                if (valid) finish_chunk(c0, f, rnext);
                 if (dbg && threadIdx.x == 0 && c0 == chunk0) dbg[42] = clock64();
             }
         } else {
@@ -471,12 +495,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             asm volatile("bar.sync 1, %0;" ::"n"(kSlim ? 128 : 256) : "memory");
             if (dbg && threadIdx.x == 0) dbg[44] = clock64();
             if (s_last) {
-                fetch_res(chunk0);
                 for (int c0 = chunk0; c0 < nvalid; c0 += kChunkStep) {
-                    uint4 rcur[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-                    if (c0 + kChunkStep < nvalid) fetch_res(c0 + kChunkStep);
+                    fetch_res(c0);
                     if (valid) {
                         float f[32];
 #pragma unroll
@@ -489,7 +509,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                 f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
                             }
                         }
-                        finish_chunk(c0, f, rcur);
+                        finish_chunk(c0, f, rnext);
                     }
                 }
                 if (threadIdx.x == 0) p.counters[tile_lin] = 0;   // ready for the next launch of this layer
@@ -796,6 +816,14 @@ bool pair_enabled() {
     return on;
 }
 
+bool dual_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("RMR_NO_DUAL");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
+
 bool slim_enabled() {
     static const bool on = [] {
         const char* e = std::getenv("RMR_NO_SLIM");
@@ -889,6 +917,7 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
         smem_total = p.na * static_cast<int>(p.a_bytes) + p.stages * static_cast<int>(p.b_bytes);
     }
     p.tmem_cols = p.block_n <= 32 ? 32u : p.block_n <= 64 ? 64u : 128u;
+    p.acc_stride = static_cast<uint32_t>((p.block_n + 31) / 32 * 32);
     // split-K: a layer whose tiles cover less than half the SMs but whose K loop is long is cut along K;
     // each split keeps at least 3 k-blocks
     {
@@ -910,6 +939,16 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
         if (p.slim) {
             p.stages = std::max(1, std::min({kMaxStages, static_cast<int>(kSmemBudgetSlim / p.stage_stride), num_it}));
             smem_total = p.stages * static_cast<int>(p.stage_stride);
+        }
+        // two MMA issue streams (wide variant, plain per-tap mode): even ring size, at least two k-blocks
+        // (pays when the layer is one wave of CTAs, i.e. latency bound; multi-wave layers already overlap CTAs)
+        p.dual = (dual_enabled() && !p.slim && !p.halo && !p.pair && splits == 1 && num_it >= 2 && p.stages >= 2 &&
+                  ctas <= 2 * 148) ? 1 : 0;
+        if (p.dual) {
+            p.stages &= ~1;
+            smem_total = p.stages * static_cast<int>(p.stage_stride);
+            const uint32_t need = 2 * p.acc_stride;
+            p.tmem_cols = need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : 256u;
         }
     }
     const int out_align = d.out_f32 ? 4 : 8;
@@ -990,26 +1029,18 @@ void conv_bind_scratch(ConvLaunch& l, void* zeroed_base) {
 void conv_init() {
     static std::once_flag once;
     std::call_once(once, [] {
-        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kSmemBudget + 1024));
-        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kSmemBudget + 1024));
-        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-        RMR_CUDA((cudaFuncSetAttribute(conv_umma_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kSmemBudgetSlim + 1024)));
-        RMR_CUDA((cudaFuncSetAttribute(conv_umma_kernel<0, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                       cudaSharedmemCarveoutMaxShared)));
-        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kSmemBudget + 1024));
-        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      2 * kSmemBudget + 1024));
-        RMR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
+        auto prep = [](auto kernel, int smem) {
+            RMR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            RMR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
+        };
+        prep(conv_umma_kernel<0, false, false>, kSmemBudget + 1024);
+        prep(conv_umma_kernel<0, false, true>, kSmemBudget + 1024);
+        prep(conv_umma_kernel<0, true, false>, kSmemBudgetSlim + 1024);
+        prep(conv_umma_kernel<0, true, true>, kSmemBudgetSlim + 1024);
+        prep(conv_umma_kernel<1>, kSmemBudget + 1024);
+        prep(conv_umma_kernel<2>, 2 * kSmemBudget + 1024);
+        prep(conv_umma_kernel<3>, kSmemBudget + 1024);
         get_encode_fn();
         const char* e = std::getenv("RMR_NO_PDL");
         g_use_pdl = !(e && e[0] == '1');
@@ -1039,11 +1070,14 @@ void launch_conv_umma(const ConvLaunch& l, cudaStream_t s, bool pdl) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    if (l.p.slim) RMR_CUDA((cudaLaunchKernelEx(&cfg, conv_umma_kernel<0, true>, l.tm_a, l.tm_b, l.p)));
-    else if (l.p.pair) RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<3>, l.tm_a, l.tm_b, l.p));
+    const bool res = l.p.res != nullptr;
+    if (l.p.pair) RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<3>, l.tm_a, l.tm_b, l.p));
     else if (l.p.halo) RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2>, l.tm_a, l.tm_b, l.p));
     else if (l.p.splits > 1) RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1>, l.tm_a, l.tm_b, l.p));
-    else RMR_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<0>, l.tm_a, l.tm_b, l.p));
+    else if (l.p.slim && res) RMR_CUDA((cudaLaunchKernelEx(&cfg, conv_umma_kernel<0, true, true>, l.tm_a, l.tm_b, l.p)));
+    else if (l.p.slim) RMR_CUDA((cudaLaunchKernelEx(&cfg, conv_umma_kernel<0, true, false>, l.tm_a, l.tm_b, l.p)));
+    else if (res) RMR_CUDA((cudaLaunchKernelEx(&cfg, conv_umma_kernel<0, false, true>, l.tm_a, l.tm_b, l.p)));
+    else RMR_CUDA((cudaLaunchKernelEx(&cfg, conv_umma_kernel<0, false, false>, l.tm_a, l.tm_b, l.p)));
 }
 
 void launch_conv_simt(const ConvDesc& d, cudaStream_t s) {

@@ -40,6 +40,8 @@ struct ConvParams {
     uint32_t idesc, sbo, layout;
     uint32_t a_bytes, b_bytes, b_off, stage_stride, tmem_cols;   // operand ring geometry
     int stages, vec_ok;
+    int dual;                            // two MMA issue streams (warps 4 and 6), two accumulators acc_stride columns apart
+    uint32_t acc_stride;
     int slim;                            // 192-thread / 3-CTAs-per-SM kernel variant
     int pair;                            // CTA-pair mode (cta_group::2): b_bytes / tm_b box hold half of the weight rows
     int halo, na;                        // halo mode (3x3 stride 1): on/off, activation patch slots (1 or 2)
