@@ -113,7 +113,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 mbar_init(smem_u32(&bar_full[i]), 1);
                 mbar_init(smem_u32(&bar_empty[i]), 1);
             }
-            mbar_init(smem_u32(&bar_acc), p.dual ? 2 : 1);
+            mbar_init(smem_u32(&bar_acc), p.dual ? p.dual : 1);
             if (kHalo)
                 for (int i = 0; i < 2; ++i) {
                     mbar_init(smem_u32(&bar_afull[i]), 1);
@@ -233,7 +233,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // ------------------------------ MMA issuer ------------------------------
         const bool leader = elect_one();
         if (!kHalo) {
-            mma_stream(0, p.dual ? 2 : 1, 0u);
+            mma_stream(0, p.dual ? p.dual : 1, 0u);
         } else {
             // Halo mode.  The activation patch of one 64-channel chunk is [18 rows][16 cols] pixels x 128 B
             // (SWIZZLE_128B as written by TMA, slot base 1024-aligned).  The A operand of tap (dy, dx) is the
@@ -323,7 +323,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
         }
-        if (!kSlim && !kHalo && warp == 6 && p.dual) mma_stream(1, 2, p.acc_stride);   // second issue stream
+        // further issue streams: warp 6 (and 7, 8 with four streams), each with its own accumulator
+        if (!kSlim && !kHalo && warp >= 6 && warp - 5 < p.dual) mma_stream(warp - 5, p.dual, (warp - 5) * p.acc_stride);
         // ---------------- epilogue: warps 0-3 and 6-9; TMEM lane quarter = warp % 4 ----------------
         // the two warps of a quarter interleave 32-column chunks (0, 64, .. / 32, 96, ..)
         const int q = warp & 3;
@@ -454,8 +455,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                if (p.dual) {   // the second issue stream's accumulator
-                    tmem_ld_32(taddr + p.acc_stride + c0, v);
+                for (int st = 1; st < p.dual; ++st) {   // the other issue streams' accumulators
+                    tmem_ld_32(taddr + st * p.acc_stride + c0, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
@@ -824,6 +825,14 @@ bool dual_enabled() {
     return on;
 }
 
+bool quad_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("RMR_NO_QUAD");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
+
 bool slim_enabled() {
     static const bool on = [] {
         const char* e = std::getenv("RMR_NO_SLIM");
@@ -945,10 +954,17 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
         p.dual = (dual_enabled() && !p.slim && !p.halo && !p.pair && splits == 1 && num_it >= 2 && p.stages >= 2 &&
                   ctas <= 2 * 148) ? 1 : 0;
         if (p.dual) {
-            p.stages &= ~1;
+            p.dual = 2;
+            // one CTA per SM anyway: the whole shared memory can hold the ring (deeper pipeline per stream)
+            // and four streams fit (their accumulators may then take all 512 TMEM columns)
+            if (ctas <= 148) {
+                p.stages = std::max(2, std::min({kMaxStages, static_cast<int>(2 * kSmemBudget / p.stage_stride), num_it}));
+                if (quad_enabled() && p.stages >= 4 && num_it >= 4) p.dual = 4;
+            }
+            p.stages &= ~(p.dual - 1);
             smem_total = p.stages * static_cast<int>(p.stage_stride);
-            const uint32_t need = 2 * p.acc_stride;
-            p.tmem_cols = need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : 256u;
+            const uint32_t need = p.dual * p.acc_stride;
+            p.tmem_cols = need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u;
         }
     }
     const int out_align = d.out_f32 ? 4 : 8;
@@ -1034,8 +1050,8 @@ void conv_init() {
             RMR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                           cudaSharedmemCarveoutMaxShared));
         };
-        prep(conv_umma_kernel<0, false, false>, kSmemBudget + 1024);
-        prep(conv_umma_kernel<0, false, true>, kSmemBudget + 1024);
+        prep(conv_umma_kernel<0, false, false>, 2 * kSmemBudget + 1024);
+        prep(conv_umma_kernel<0, false, true>, 2 * kSmemBudget + 1024);
         prep(conv_umma_kernel<0, true, false>, kSmemBudgetSlim + 1024);
         prep(conv_umma_kernel<0, true, true>, kSmemBudgetSlim + 1024);
         prep(conv_umma_kernel<1>, kSmemBudget + 1024);

@@ -40,7 +40,7 @@ struct ConvParams {
     uint32_t idesc, sbo, layout;
     uint32_t a_bytes, b_bytes, b_off, stage_stride, tmem_cols;   // operand ring geometry
     int stages, vec_ok;
-    int dual;                            // two MMA issue streams (warps 4 and 6), two accumulators acc_stride columns apart
+    int dual;                            // MMA issue streams: 0/1 = one (warp 4), 2 = +warp 6, 4 = +warps 7, 8; accumulators acc_stride columns apart
     uint32_t acc_stride;
     int slim;                            // 192-thread / 3-CTAs-per-SM kernel variant
     int pair;                            // CTA-pair mode (cta_group::2): b_bytes / tm_b box hold half of the weight rows
