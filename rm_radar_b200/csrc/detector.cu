@@ -143,7 +143,9 @@ std::vector<std::vector<Detection>> Detector::run(const uint8_t* dev_frame, int 
         const int c = std::min(pinned_counts_[i], kMaxOut);
         results[i].assign(pinned_out_ + static_cast<size_t>(i) * kMaxOut, pinned_out_ + static_cast<size_t>(i) * kMaxOut + c);
     }
-    last_launches_ = (any_clean ? 1 : 0) + (any_unclean ? 2 : 0) + net_->launches_per_forward() + 2;
+    int net_launches = 0;
+    net_->plan_stats(n, &net_launches, nullptr, nullptr);
+    last_launches_ = (any_clean ? 1 : 0) + (any_unclean ? 2 : 0) + net_launches + 2;
     return results;
 }
 
