@@ -2,8 +2,9 @@
 """bench.py — detect + locate frames/s of the B200-native hot path (BASELINE.json metric).
 
 Workload at N=1: BASELINE config[1] "single 1920x1080 frame + 100k-pt cloud, car+armor cascade,
-1xB200": one step = Locator.update + cluster, RobotDetector.detect (car net, per-ROI armor net),
-Locator.search for ONE frame, synchronously (latency mode, like SampleRadar::runOnce).
+1xB200": one step = one `rmr_run_once` call = SampleRadar::runOnce for ONE frame, synchronously (latency
+mode): Locator.update + cluster overlapped with RobotDetector.detect (car net, per-ROI armor net), then
+Locator.search.
 N>1: one process per GPU (torchrun), one independent camera+LiDAR stream per rank (weak scaling,
 BASELINE config[3]) and one NCCL all-gather of the fixed-size robot position block per step.
 
@@ -217,20 +218,16 @@ def run_ours(args, rank, world, local_rank):
     def step_resident(i):
         j = i % POOL
         loc_stream.wait_stream(stream)      # the cloud of step i is not touched before step i-1 is done
-        loc.update_device(clouds_dev[j].data_ptr(), NPTS, 12)
-        loc.cluster()
-        recs, n = det.detect_records(frames_dev[j].data_ptr(), W, H, W * 3, device_ptr=True)
-        loc.search_records(recs, n)
+        recs, n = rr.run_once_records(det, loc, frames_dev[j].data_ptr(), True, W, H, W * 3,
+                                      clouds_dev[j].data_ptr(), True, NPTS, 12)
         publish(recs, n)
         return n
 
     def step_e2e(i):
         j = i % POOL
         loc_stream.wait_stream(stream)
-        _lib.check(lib.rmr_locator_update(loc._h, ctypes.c_void_p(clouds_pin[j].data_ptr()), NPTS, 12))
-        loc.cluster()
-        recs, n = det.detect_records(frames_pin[j].data_ptr(), W, H, W * 3, device_ptr=False)
-        loc.search_records(recs, n)
+        recs, n = rr.run_once_records(det, loc, frames_pin[j].data_ptr(), False, W, H, W * 3,
+                                      clouds_pin[j].data_ptr(), False, NPTS, 12)
         publish(recs, n)
         return n
 

@@ -393,4 +393,19 @@ class Locator {
     rmr_locator_t* handle_ = nullptr;
 };
 
+// One frame of the whole path — the body of SampleRadar::runOnce (samples/sample_radar.h:106-127) without the
+// tracker and the GUI: Locator::update + cluster overlap with RobotDetector::detect, then Locator::search.
+inline std::vector<Robot> runOnce(RobotDetector& detector, Locator& locator, const ImageView& image,
+                                  const CloudView& cloud, int max_robots = 64) {
+    std::vector<rmr_robot_t> recs(static_cast<size_t>(max_robots));
+    int n = 0;
+    const int stride = image.stride_bytes ? image.stride_bytes : image.width * 3;
+    if (rmr_run_once(detector.handle(), locator.handle(), image.data, 0, image.width, image.height, stride, cloud.xyz, 0,
+                     cloud.size, cloud.stride_bytes, recs.data(), max_robots, &n) != RMR_OK)
+        detail::fatal("runOnce");
+    std::vector<Robot> robots;
+    for (int i = 0; i < n && i < max_robots; ++i) robots.push_back(Robot::fromRecord(recs[static_cast<size_t>(i)]));
+    return robots;
+}
+
 }  // namespace radar

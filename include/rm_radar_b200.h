@@ -139,6 +139,16 @@ int rmr_locator_read_image(rmr_locator_t* l, int which, void* out);
 int rmr_locator_stats(rmr_locator_t* l, int* n_foreground, int* n_clusters);
 int rmr_locator_read_foreground(rmr_locator_t* l, float* xyz_pix, int capacity); /* [n][4]: x,y,z,pixel */
 
+/* ---- one frame of the whole path — SampleRadar::runOnce, samples/sample_radar.h:106-127 (without the
+ * tracker and the GUI).  The reference runs Locator::update + cluster and RobotDetector::detect on two
+ * std::async threads and joins before Locator::search; here one host thread enqueues the car stage, then the
+ * locator's work on the locator's own stream, and only then waits — same overlap, no thread hand-off.
+ * `frame` / `xyz` are host pointers, or device pointers when the *_on_device flag is set.
+ * The detector and the locator must live on the same device and use different streams (the default). */
+int rmr_run_once(rmr_robot_detector_t* d, rmr_locator_t* l, const void* frame, int frame_on_device, int width, int height,
+                 int stride_bytes, const void* xyz, int cloud_on_device, int n_points, int point_stride_bytes,
+                 rmr_robot_t* out, int capacity, int* count);
+
 /* ---- conv layer self-test (tests/bench only): tcgen05 path vs the CUDA-core checker --------- */
 /* runs one conv of the given shape on random data through both kernels on the current device and
  * returns the max abs difference; also times the tcgen05 kernel (ms per launch over `iters`). */

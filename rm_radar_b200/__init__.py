@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import RadarError  # noqa: F401
 
 __all__ = ["Detector", "RobotDetector", "Locator", "Robot", "Detection", "Label", "RadarError",
-           "engine_path_for"]
+           "engine_path_for", "run_once", "run_once_records"]
 
 
 class Label(enum.IntEnum):
@@ -373,6 +373,25 @@ class Locator:
 
     def set_stream(self, cuda_stream: int):
         _lib.check(self._lib.rmr_locator_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+
+def run_once_records(detector: "RobotDetector", locator: "Locator", frame_ptr: int, frame_on_device: bool, width: int,
+                     height: int, stride: int, cloud_ptr: int, cloud_on_device: bool, n_points: int, point_stride: int):
+    """SampleRadar::runOnce (sample_radar.h:106-127) on raw pointers: returns (ctypes RobotRec array, count)."""
+    n = C.c_int()
+    _lib.check(detector._lib.rmr_run_once(detector._h, locator._h, C.c_void_p(frame_ptr), int(frame_on_device), width,
+                                          height, stride, C.c_void_p(cloud_ptr), int(cloud_on_device), n_points,
+                                          point_stride, detector._recs, detector.max_cars, C.byref(n)))
+    return detector._recs, min(n.value, detector.max_cars)
+
+
+def run_once(detector: "RobotDetector", locator: "Locator", image: np.ndarray, cloud) -> list:
+    """One frame of the whole path on host arrays: detect + update + cluster + search -> list[Robot]."""
+    img = _as_bgr(image)
+    pts = np.ascontiguousarray(np.asarray(cloud, np.float32)[:, :3]) if cloud is not None and len(cloud) else None
+    recs, n = run_once_records(detector, locator, img.ctypes.data, False, img.shape[1], img.shape[0], img.strides[0],
+                               pts.ctypes.data if pts is not None else 0, False, len(pts) if pts is not None else 0, 12)
+    return [_robot_from_rec(recs[i]) for i in range(n)]
 
 
 def conv_selftest(n, h, w, cin, cout, k, stride, act=1, residual=0, out_f32=0, seed=0, iters=0):

@@ -39,7 +39,7 @@ SYMBOLS = [
     "rmr_locator_create", "rmr_locator_destroy", "rmr_locator_update", "rmr_locator_update_device",
     "rmr_locator_cluster", "rmr_locator_search", "rmr_locator_set_stream", "rmr_locator_image_size",
     "rmr_locator_read_image", "rmr_locator_stats", "rmr_locator_read_foreground",
-    "rmr_conv_selftest", "rmr_conv_timeline",
+    "rmr_run_once", "rmr_conv_selftest", "rmr_conv_timeline",
 ]
 
 _lib = None
@@ -101,6 +101,7 @@ def load():
     lib.rmr_locator_stats.argtypes = [vp, P(ci), P(ci)]
     lib.rmr_locator_read_foreground.argtypes = [vp, vp, ci]
     lib.rmr_conv_selftest.argtypes = [ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, C.c_uint, ci, P(cf), P(cf), P(cf)]
+    lib.rmr_run_once.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, ci, ci, ci, P(RobotRec), ci, P(ci)]
     lib.rmr_conv_timeline.argtypes = [ci, ci, ci, ci, ci, ci, ci, vp, ci, P(ci)]
     _lib = lib
     return lib

@@ -356,6 +356,45 @@ int rmr_locator_read_foreground(rmr_locator_t* l, float* xyz_pix, int capacity) 
     });
 }
 
+// ---------------------------------------------------------------- one frame (SampleRadar::runOnce)
+int rmr_run_once(rmr_robot_detector_t* d, rmr_locator_t* l, const void* frame, int frame_on_device, int width, int height,
+                 int stride_bytes, const void* xyz, int cloud_on_device, int n_points, int point_stride_bytes,
+                 rmr_robot_t* out, int capacity, int* count) {
+    return guarded([&] {
+        if (!d || !l || !out || !count) throw std::invalid_argument("null argument");
+        if (xyz && (point_stride_bytes % 4 != 0 || point_stride_bytes < 12)) throw std::invalid_argument("bad point stride");
+        // 1. car stage goes out first (upload + letterbox + network + decode/NMS + D2H), nothing waits
+        d->impl->begin(static_cast<const uint8_t*>(frame), frame_on_device != 0, width, height, stride_bytes);
+        // 2. the locator's launches are issued while the car network runs (its own stream)
+        RMR_CUDA(cudaSetDevice(l->device));
+        if (cloud_on_device) l->impl->update_device(static_cast<const float*>(xyz), n_points, point_stride_bytes / 4, l->stream);
+        else l->impl->update_host(static_cast<const float*>(xyz), n_points, point_stride_bytes / 4, l->stream);
+        l->impl->cluster(l->stream);
+        // 3. car results -> armor stage -> robots
+        auto robots = d->impl->finish();
+        *count = static_cast<int>(robots.size());
+        const int n = std::min<int>(*count, capacity);
+        for (int i = 0; i < n; ++i) fill_robot(robots[i], out + i);
+        // 4. Locator::search on the records
+        if (n > 0) {
+            std::vector<RectF> rects(n);
+            std::vector<LocResult> res(n);
+            for (int i = 0; i < n; ++i)
+                rects[i] = RectF{out[i].rect[0], out[i].rect[1], out[i].rect[2], out[i].rect[3], out[i].has_rect};
+            l->impl->search(rects.data(), res.data(), n, l->stream);
+            for (int i = 0; i < n; ++i) {
+                if (!res[i].located) continue;
+                out[i].is_located = 1;
+                out[i].location[0] = res[i].x; out[i].location[1] = res[i].y; out[i].location[2] = res[i].z;
+                out[i].cluster = res[i].cluster;
+                out[i].cluster_points = res[i].npoints;
+            }
+        } else {
+            RMR_CUDA(cudaStreamSynchronize(l->stream));
+        }
+    });
+}
+
 // ---------------------------------------------------------------- conv self-test
 int rmr_conv_selftest(int n, int h_in, int w_in, int cin, int cout, int k, int stride, int act, int residual,
                       int out_f32, unsigned seed, int iters, float* max_abs_diff, float* max_ref, float* ms) {

@@ -113,9 +113,12 @@ uint8_t* Detector::frame_buffer(size_t bytes) {
     return dev_frame_;
 }
 
-std::vector<std::vector<Detection>> Detector::run(const uint8_t* dev_frame, int stride, const Roi* rois, int n) {
-    std::vector<std::vector<Detection>> results(n);
-    if (n == 0) return results;   // Appendix B#8: the reference aborts inside TensorRT on an empty batch
+// enqueue(): everything up to the device->host copy of the survivors, asynchronously on stream_;
+// collect(): the one synchronisation + unpacking.  run() = enqueue + collect; the cascade uses the split
+// to overlap its own CPU work (and the Locator's launches) with the car network.
+void Detector::enqueue(const uint8_t* dev_frame, int stride, const Roi* rois, int n) {
+    pending_ = 0;
+    if (n == 0) return;   // Appendix B#8: the reference aborts inside TensorRT on an empty batch
     if (n > max_batch_) throw std::invalid_argument("batch larger than max_batch_size");
     RMR_CUDA(cudaSetDevice(device_));
     bool any_clean = false, any_unclean = false;
@@ -138,15 +141,29 @@ std::vector<std::vector<Detection>> Detector::run(const uint8_t* dev_frame, int 
     launch_postprocess(net_->levels(), classes_, n, dev_geoms_, conf_thresh_, nms_thresh_, post_, stream_);
     RMR_CUDA(cudaMemcpyAsync(pinned_counts_, post_.out_count, sizeof(int) * n, cudaMemcpyDeviceToHost, stream_));
     RMR_CUDA(cudaMemcpyAsync(pinned_out_, post_.out, sizeof(Detection) * kMaxOut * n, cudaMemcpyDeviceToHost, stream_));
+    int net_launches = 0;
+    net_->plan_stats(n, &net_launches, nullptr, nullptr);
+    last_launches_ = (any_clean ? 1 : 0) + (any_unclean ? 2 : 0) + net_launches + 2;
+    pending_ = n;
+}
+
+std::vector<std::vector<Detection>> Detector::collect() {
+    const int n = pending_;
+    pending_ = 0;
+    std::vector<std::vector<Detection>> results(n);
+    if (n == 0) return results;
+    RMR_CUDA(cudaSetDevice(device_));
     RMR_CUDA(cudaStreamSynchronize(stream_));
     for (int i = 0; i < n; ++i) {
         const int c = std::min(pinned_counts_[i], kMaxOut);
         results[i].assign(pinned_out_ + static_cast<size_t>(i) * kMaxOut, pinned_out_ + static_cast<size_t>(i) * kMaxOut + c);
     }
-    int net_launches = 0;
-    net_->plan_stats(n, &net_launches, nullptr, nullptr);
-    last_launches_ = (any_clean ? 1 : 0) + (any_unclean ? 2 : 0) + net_launches + 2;
     return results;
+}
+
+std::vector<std::vector<Detection>> Detector::run(const uint8_t* dev_frame, int stride, const Roi* rois, int n) {
+    enqueue(dev_frame, stride, rois, n);
+    return collect();
 }
 
 std::vector<Detection> Detector::detect_host(const uint8_t* bgr, int w, int h, int stride) {
@@ -287,23 +304,46 @@ RobotDetector::RobotDetector(const std::string& car_engine, const std::string& a
     armor_->set_stream(car_->stream());
 }
 
-std::vector<RobotRecord> RobotDetector::detect_host(const uint8_t* bgr, int w, int h, int stride) {
-    if (!bgr || w <= 0 || h <= 0 || stride < w * 3) throw std::invalid_argument("bad image");
+// begin(): upload (host frames) and enqueue the car stage, nothing waits; finish(): the rest of
+// RobotDetector::detect (detector.cpp:413-455).  detect_host / detect_device = begin + finish.
+void RobotDetector::begin(const uint8_t* frame, bool on_device, int w, int h, int stride) {
+    if (!frame || w <= 0 || h <= 0 || stride < w * 3) throw std::invalid_argument("bad image");
     RMR_CUDA(cudaSetDevice(car_->device()));
-    const size_t bytes = static_cast<size_t>(w) * h * 3;
-    uint8_t* dev = car_->frame_buffer(bytes);
-    if (stride == w * 3) {
-        RMR_CUDA(cudaMemcpyAsync(dev, bgr, bytes, cudaMemcpyHostToDevice, car_->stream()));
-    } else {
-        RMR_CUDA(cudaMemcpy2DAsync(dev, static_cast<size_t>(w) * 3, bgr, stride, static_cast<size_t>(w) * 3, h,
-                                   cudaMemcpyHostToDevice, car_->stream()));
+    const uint8_t* dev = frame;
+    int dev_stride = stride;
+    if (!on_device) {
+        const size_t bytes = static_cast<size_t>(w) * h * 3;
+        uint8_t* buf = car_->frame_buffer(bytes);
+        if (stride == w * 3) {
+            RMR_CUDA(cudaMemcpyAsync(buf, frame, bytes, cudaMemcpyHostToDevice, car_->stream()));
+        } else {
+            RMR_CUDA(cudaMemcpy2DAsync(buf, static_cast<size_t>(w) * 3, frame, stride, static_cast<size_t>(w) * 3, h,
+                                       cudaMemcpyHostToDevice, car_->stream()));
+        }
+        dev = buf;
+        dev_stride = w * 3;
     }
-    return detect_device(dev, w, h, w * 3);
+    cur_frame_ = dev; cur_w_ = w; cur_h_ = h; cur_stride_ = dev_stride;
+    const Roi full{0, 0, w, h};
+    car_->enqueue(dev, dev_stride, &full, 1);
+}
+
+std::vector<RobotRecord> RobotDetector::detect_host(const uint8_t* bgr, int w, int h, int stride) {
+    begin(bgr, false, w, h, stride);
+    return finish();
 }
 
 std::vector<RobotRecord> RobotDetector::detect_device(const uint8_t* dev_bgr, int w, int h, int stride) {
-    const Roi full{0, 0, w, h};
-    std::vector<Detection> cars = car_->detect_device_rois(dev_bgr, stride, &full, 1)[0];
+    begin(dev_bgr, true, w, h, stride);
+    return finish();
+}
+
+std::vector<RobotRecord> RobotDetector::finish() {
+    const uint8_t* dev_bgr = cur_frame_;
+    const int stride = cur_stride_;
+    if (dev_bgr == nullptr) throw std::invalid_argument("RobotDetector::finish without begin");
+    cur_frame_ = nullptr;
+    std::vector<Detection> cars = car_->collect()[0];
     last_launches_ = car_->last_launches();
     last_flops_ = car_->net().flops_per_image();
     // Appendix B#8: more cars than max_batch_size is UB in the reference; keep the first max_cars

@@ -30,6 +30,9 @@ public:
     // ROIs of a frame that already lives in device memory (the cascade's second stage)
     std::vector<std::vector<Detection>> detect_device_rois(const uint8_t* dev_frame, int stride, const Roi* rois,
                                                            int n);
+    // asynchronous halves of detect_device_rois (same stream): enqueue everything, then wait + unpack
+    void enqueue(const uint8_t* dev_frame, int stride, const Roi* rois, int n);
+    std::vector<std::vector<Detection>> collect();
     void last_input(float* out, int n);    // [n][3][H][W] float
     void last_output(float* out, int n);   // [n][4+nc][A] float
     void set_stream(cudaStream_t s) { stream_ = s; }
@@ -43,6 +46,7 @@ public:
 
 private:
     std::vector<std::vector<Detection>> run(const uint8_t* dev_frame, int stride, const Roi* rois, int n);
+    int pending_ = 0;
 
     int classes_, image_w_, image_h_, max_batch_, input_w_, input_h_, device_;
     float nms_thresh_, conf_thresh_;
@@ -76,6 +80,9 @@ public:
                   float armor_conf, int input_w, int input_h, bool compat, int device);
     std::vector<RobotRecord> detect_host(const uint8_t* bgr, int w, int h, int stride);
     std::vector<RobotRecord> detect_device(const uint8_t* dev_bgr, int w, int h, int stride);
+    // split form: begin() uploads / enqueues the car stage and returns at once, finish() does the rest
+    void begin(const uint8_t* frame, bool on_device, int w, int h, int stride);
+    std::vector<RobotRecord> finish();
     void set_stream(cudaStream_t s) { car_->set_stream(s); armor_->set_stream(s); }
     Detector& car() { return *car_; }
     Detector& armor() { return *armor_; }
@@ -92,6 +99,8 @@ private:
     std::vector<std::vector<Detection>> last_armors_;
     int last_launches_ = 0;
     double last_flops_ = 0;
+    const uint8_t* cur_frame_ = nullptr;
+    int cur_w_ = 0, cur_h_ = 0, cur_stride_ = 0;
 };
 
 }  // namespace rmr

@@ -55,7 +55,25 @@ int main(int argc, char** argv) {
         detector.detect(radar::ImageView{reinterpret_cast<const unsigned char*>(frame.data()), W, H, W * 3});
     locator.search(robots);
 
-    std::printf("{\"ctor_throws\": %s, \"robots\": [", threw ? "true" : "false");
+    // the fused entry point must give the same robots on the same inputs (fresh objects: same locator history)
+    bool run_once_same = true;
+    {
+        radar::RobotDetector det2(argv[1], argv[2], radar::Size{W, H}, 12, 20, 4);
+        radar::Locator loc2(W, H, K, L2C, W2C);
+        loc2.update(radar::CloudView{reinterpret_cast<const float*>(bg.data()), static_cast<int>(bg.size() / 12), 12});
+        std::vector<radar::Robot> r2 = radar::runOnce(
+            det2, loc2, radar::ImageView{reinterpret_cast<const unsigned char*>(frame.data()), W, H, W * 3},
+            radar::CloudView{reinterpret_cast<const float*>(cloud.data()), static_cast<int>(cloud.size() / 12), 12});
+        run_once_same = r2.size() == robots.size();
+        for (size_t i = 0; run_once_same && i < robots.size(); ++i) {
+            run_once_same = r2[i].label() == robots[i].label() && r2[i].isLocated() == robots[i].isLocated() &&
+                            r2[i].rectf()->x == robots[i].rectf()->x && r2[i].rectf()->width == robots[i].rectf()->width;
+            if (run_once_same && robots[i].isLocated())
+                run_once_same = r2[i].location()->x == robots[i].location()->x && r2[i].location()->z == robots[i].location()->z;
+        }
+    }
+    std::printf("{\"ctor_throws\": %s, \"run_once_same\": %s, \"robots\": [", threw ? "true" : "false",
+                run_once_same ? "true" : "false");
     for (size_t i = 0; i < robots.size(); ++i) {
         const radar::Robot& r = robots[i];
         const auto rf = r.rectf().value();

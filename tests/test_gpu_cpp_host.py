@@ -28,6 +28,7 @@ def test_cpp_host_run_once(tmp_path):
     assert out.returncode == 0, out.stderr
     doc = json.loads(out.stdout)
     assert doc["ctor_throws"] is True
+    assert doc["run_once_same"] is True      # radar::runOnce == update + cluster + detect + search
     robots = doc["robots"]
     rects = np.array([r["rect"] for r in robots], np.float32)
     assert len(rects) == len(exp["f0_robot_rects"])
