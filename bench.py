@@ -152,6 +152,10 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     frame, bg, cloud, fx = make_inputs(1)
+    if not fx.have_onnx():
+        print(json.dumps({"impl": "reference", "unavailable": "fp32 ONNX copies (rm_radar_b200/engines/*.onnx) are not in "
+                          "this snapshot; run __graft_entry__.build() where /root/reference is mounted"}), flush=True)
+        return
     r = cpu_path(frame, bg, cloud, fx, budget_s=120.0, max_frames=max(1, args.steps))
     line = {"impl": "reference", "metric": "detect+locate frames/sec", "value": r["value"], "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
