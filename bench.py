@@ -92,7 +92,7 @@ class ClockSampler:
 
 def ncu_traffic():
     """dram bytes per launch of the dominant kernel from the committed `ncu --set full` summary
-    (profiles/*_conv_full.json, written by tools_ncu_summary.py); None when no capture is committed."""
+    (profiles/*_conv_full.json, written by tools/ncu_summary.py); None when no capture is committed."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_conv_full.json")))
     if not files:

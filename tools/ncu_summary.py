@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Digest ncu output into the small files kept under profiles/.
 
-  python tools_ncu_summary.py launches <launches.csv> <out.md>      per-kernel totals / shares of one bench step
-  python tools_ncu_summary.py full <raw.csv> <out.json> <out.md>    key metrics of an `ncu --set full` capture
+  python tools/ncu_summary.py launches <launches.csv> <out.md>      per-kernel totals / shares of one bench step
+  python tools/ncu_summary.py full <raw.csv> <out.json> <out.md>    key metrics of an `ncu --set full` capture
                                                                     (raw.csv = `ncu -i rep --page raw --csv`)
 """
 import collections

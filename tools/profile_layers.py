@@ -1,9 +1,13 @@
 #!/usr/bin/env python
 """Per-layer table of the two conv stacks on the GPU: shape, path, ms, achieved TFLOP/s.
-Usage: python tools_profile_layers.py [armor_batch] > gpurun_out/layers.txt"""
+Usage: python tools/profile_layers.py [armor_batch] > gpurun_out/layers.txt"""
 import sys
 
-import rm_radar_b200 as rr
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rm_radar_b200 as rr  # noqa: E402
 from tests import fixtures as fx
 
 kb = int(sys.argv[1]) if len(sys.argv) > 1 else 7

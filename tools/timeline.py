@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Prints the per-CTA phase timeline (SM cycles) of the tcgen05 conv kernel for a few layer shapes."""
 import numpy as np
-import rm_radar_b200 as rr
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rm_radar_b200 as rr  # noqa: E402
 
 import sys
 SHAPES = [(1, 160, 160, 64, 64, 3, 1), (1, 160, 160, 64, 1, 1, 1), (1, 20, 20, 512, 64, 3, 1), (1, 40, 40, 128, 128, 3, 1),
