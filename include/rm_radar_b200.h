@@ -132,6 +132,10 @@ int rmr_locator_update_device(rmr_locator_t* l, const void* dev_xyz, int n_point
 int rmr_locator_cluster(rmr_locator_t* l);
 /* Locator::search(std::vector<Robot>&)  locate.cpp:276-326: fills is_located / location */
 int rmr_locator_search(rmr_locator_t* l, rmr_robot_t* robots, int n_robots);
+/* background persistence: the running-max background depth image (locate.cpp:188-191) is the
+ * only long-lived Locator state; the reference re-derives it from background.pcd at every start
+ * (samples/README.md:3).  save = rmr_locator_read_image(l, 1, out); load replaces it (float [Hz][Wz], zoomed size). */
+int rmr_locator_load_background(rmr_locator_t* l, const float* image, int width, int height);
 int rmr_locator_set_stream(rmr_locator_t* l, void* cuda_stream);
 /* inspection for parity tests.  which: 0 depth, 1 background, 2 diff (float), 3 cluster-label image (int32) */
 int rmr_locator_image_size(rmr_locator_t* l, int* width, int* height);

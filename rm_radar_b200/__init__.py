@@ -360,6 +360,14 @@ class Locator:
         _lib.check(self._lib.rmr_locator_read_image(self._h, idx, out.ctypes.data))
         return out
 
+    def save_background(self) -> np.ndarray:
+        """The running-max background depth image (the only long-lived Locator state)."""
+        return self.image("background")
+
+    def load_background(self, image: np.ndarray):
+        img = np.ascontiguousarray(image, np.float32)
+        _lib.check(self._lib.rmr_locator_load_background(self._h, img.ctypes.data, img.shape[1], img.shape[0]))
+
     def stats(self):
         f, c = C.c_int(), C.c_int()
         _lib.check(self._lib.rmr_locator_stats(self._h, C.byref(f), C.byref(c)))

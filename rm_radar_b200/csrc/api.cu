@@ -320,6 +320,16 @@ int rmr_locator_search(rmr_locator_t* l, rmr_robot_t* robots, int n_robots) {
         }
     });
 }
+int rmr_locator_load_background(rmr_locator_t* l, const float* image, int width, int height) {
+    return guarded([&] {
+        if (!l || !image) throw std::invalid_argument("null argument");
+        if (width != l->impl->wz() || height != l->impl->hz())
+            throw std::invalid_argument("background image size does not match the zoomed depth image");
+        RMR_CUDA(cudaSetDevice(l->device));
+        RMR_CUDA(cudaStreamSynchronize(l->stream));
+        RMR_CUDA(cudaMemcpy(l->impl->background_image_mut(), image, sizeof(float) * width * height, cudaMemcpyHostToDevice));
+    });
+}
 int rmr_locator_set_stream(rmr_locator_t* l, void* cuda_stream) {
     return guarded([&] { l->stream = static_cast<cudaStream_t>(cuda_stream); });
 }

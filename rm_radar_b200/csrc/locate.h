@@ -62,6 +62,7 @@ public:
     // inspection (tests): device pointers
     const float* depth_image() const;
     const float* background_image() const { return bg_; }
+    float* background_image_mut() { return bg_; }
     const float* diff_image() const { return diff_; }
     const int* label_image() const { return label_img_; }
     const float* fg_points() const { return fg_pts_; }

@@ -148,3 +148,41 @@ def test_detector_batch_and_edge_cases():
     # a black frame: no cars -> empty armor batch (the reference aborts inside TensorRT here, B#8)
     rd = rr.RobotDetector(fx.engine("car"), fx.engine("armor"), (640, 480), 12, 20, 4)
     assert rd.detect(np.zeros((480, 640, 3), np.uint8)) == []
+
+
+@needs_models
+def test_batch_of_real_frames_equals_single_calls():
+    """BASELINE config C3 geometry (1280x1280 frames, batch): Detector.detect(list) gives every image the
+    detections the single-image call gives it (different batch plans / tile shapes, same results)."""
+    det = rr.Detector(fx.engine("car"), 1, (1280, 1280), 4)
+    f0 = fx.resize_frame(fx.load_frame(0), 1280, 1280)
+    f5 = fx.resize_frame(fx.load_frame(5), 1280, 1280)
+    imgs = [f0, f5, np.ascontiguousarray(f0[:, ::-1]), f5]
+    batch = det.detect(imgs)
+    assert len(batch) == 4 and len(batch[0]) >= 4
+    for img, dets in zip(imgs, batch):
+        single = det.detect(img)
+        fx.match_detections([d.as_array() for d in dets], [d.as_array() for d in single])
+    assert [d.as_array().tolist() for d in batch[1]] == [d.as_array().tolist() for d in batch[3]]   # same image, same slot-independent result
+
+
+@needs_models
+def test_run_once_equals_separate_calls():
+    """rmr_run_once (SampleRadar::runOnce body) == update + cluster + detect + search on the same inputs."""
+    img = fx.load_frame(0)
+    clouds = fx.load_clouds()
+    kw = dict(device=0)
+    det_a = rr.RobotDetector(fx.engine("car"), fx.engine("armor"), fx.IMAGE_SIZE, fx.CLASS_NUM, fx.MAX_BATCH, fx.OPT_BATCH, **kw)
+    det_b = rr.RobotDetector(fx.engine("car"), fx.engine("armor"), fx.IMAGE_SIZE, fx.CLASS_NUM, fx.MAX_BATCH, fx.OPT_BATCH, **kw)
+    loc_a = rr.Locator(*fx.IMAGE_SIZE, fx.INTRINSIC, fx.LIDAR_TO_CAMERA, fx.WORLD_TO_CAMERA)
+    loc_b = rr.Locator(*fx.IMAGE_SIZE, fx.INTRINSIC, fx.LIDAR_TO_CAMERA, fx.WORLD_TO_CAMERA)
+    loc_a.update(clouds["background"]); loc_b.update(clouds["background"])
+    for key in ("c0", "c1"):
+        loc_a.update(clouds[key]); loc_a.cluster()
+        want = det_a.detect(img)
+        loc_a.search(want)
+        got = rr.run_once(det_b, loc_b, img, clouds[key])
+        assert len(got) == len(want) and any(r.location is not None for r in got)
+        for g, w in zip(got, want):
+            assert g.rect == w.rect and g.label == w.label and g.confidence == w.confidence
+            assert g.location == w.location and g.cluster == w.cluster

@@ -153,3 +153,22 @@ def test_queue_ordering_newest_wins():
         c = one(d) if d else np.array([[1.5, 1.5, 1.0]], np.float32)
         dev.update(c); ora.update(c)
         assert_same_state(dev, ora, labels=False)
+
+
+def test_background_save_and_restore():
+    """a Locator warm-started from a saved background image behaves like the oracle whose
+    background was set to the same image (no priming cloud in the depth ring)."""
+    clouds = fx.load_clouds()
+    primed, _ = pair(*fx.IMAGE_SIZE, fx.INTRINSIC, fx.LIDAR_TO_CAMERA, fx.WORLD_TO_CAMERA)
+    primed.update(clouds["background"])
+    saved = primed.save_background()
+    assert (saved > 0).sum() > 1000
+    dev, ora = pair(*fx.IMAGE_SIZE, fx.INTRINSIC, fx.LIDAR_TO_CAMERA, fx.WORLD_TO_CAMERA)
+    dev.load_background(saved)
+    ora.background[...] = saved
+    for key in ("c0", "c1", "c2"):
+        dev.update(clouds[key]); ora.update(clouds[key])
+        dev.cluster(); ora.cluster()
+        assert_same_state(dev, ora)
+    with pytest.raises(ValueError):
+        dev.load_background(saved[:-1])
