@@ -12,9 +12,10 @@
 //   * the TMA box lands in shared memory as 128 pixel rows x BK fp16 (128 B or 64 B per row,
 //     hardware swizzled), which is exactly the K-major SWIZZLE_128B / SWIZZLE_64B UMMA operand.
 //   * W tiles [BLOCK_N][BK] come from a 2-D tensor map over the packed [Cout_pad][taps*Cin] weights.
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue:
+//   * warp roles, issue streams, kernel variants and the optional modes (halo tile, split-K, CTA pair)
+//     are described at the kernel below; the epilogue is
 //     tcgen05.ld -> +bias -> SiLU -> +residual -> fp16 (or fp32 for the head logits) -> NHWC store at
-//     the destination channel offset (Concat is just this offset).
+//     the destination channel offset (Concat is just this offset), optionally to a second destination.
 #include "conv.h"
 
 #include <algorithm>
@@ -56,9 +57,10 @@ __device__ __forceinline__ float rcp_approx(float x) {
 
 // Warp roles: warps 0-3 = activation (A) TMA producers (ring slots round-robin) and, once their loads are
 // out, epilogue; warps 6-9 = epilogue only (two warps per TMEM lane quarter, interleaved column chunks);
-// warp 4 = MMA issuer (+ TMEM owner); warp 5 = weight (B) TMA producer.  A 5-D UTMALDG costs ~200 issue cycles on the issuing thread and a 2-D one ~60
-// (tools/tma_bench2.cu; issue cost is per warp, not a shared unit), while a 128x64x64 MMA block is only
-// 128 tensor cycles: one producer thread cannot feed the tensor core, four can.  Producer and issuer
+// warp 4 = MMA issuer (+ TMEM owner; warps 6-8 issue further MMA streams first when the layer runs two
+// or four of them); warp 5 = weight (B) TMA producer.  A 5-D UTMALDG costs ~200 issue cycles on the
+// issuing thread and a 2-D one ~60 (tools/tma_bench2.cu; issue cost is per warp, not a shared unit),
+// while a 128x64x64 MMA block is only 128 tensor cycles: one producer thread cannot feed the tensor core, four can.  Producer and issuer
 // loops run warp-converged (one elected lane issues) so the bookkeeping stays in the uniform datapath;
 // two CTAs per SM let one CTA's epilogue hide behind the other's main loop.
 // kMode 0: one TMA box per filter tap; 1: + split-K; 2: halo tile (3x3 stride 1); 3: CTA pair (cta_group::2).
