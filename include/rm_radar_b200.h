@@ -15,6 +15,7 @@
 #ifndef RM_RADAR_B200_H
 #define RM_RADAR_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -132,6 +133,12 @@ int rmr_locator_update_device(rmr_locator_t* l, const void* dev_xyz, int n_point
 int rmr_locator_cluster(rmr_locator_t* l);
 /* Locator::search(std::vector<Robot>&)  locate.cpp:276-326: fills is_located / location */
 int rmr_locator_search(rmr_locator_t* l, rmr_robot_t* robots, int n_robots);
+/* PCD ingestion: the reference reads its clouds with pcl::io::loadPCDFile
+ * (samples/main.cpp:42-72).  `file_bytes` is the whole file image (PCD v0.7, DATA ascii or binary, FIELDS
+ * containing x y z); the body is parsed on the device and fed to Locator::update without a host-side cloud. */
+int rmr_locator_update_pcd(rmr_locator_t* l, const void* file_bytes, size_t size, int* n_points);
+/* the same parser with the points copied back (tests, tools): xyz = float [capacity][3] on the host */
+int rmr_pcd_parse(const void* file_bytes, size_t size, float* xyz, int capacity, int* n_points, int device);
 /* background persistence: the running-max background depth image (locate.cpp:188-191) is the
  * only long-lived Locator state; the reference re-derives it from background.pcd at every start
  * (samples/README.md:3).  save = rmr_locator_read_image(l, 1, out); load replaces it (float [Hz][Wz], zoomed size). */

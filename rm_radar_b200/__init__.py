@@ -325,6 +325,12 @@ class Locator:
             pts = np.ascontiguousarray(pts[:, :3], np.float32)
         _lib.check(self._lib.rmr_locator_update(self._h, pts.ctypes.data, pts.shape[0], pts.strides[0]))
 
+    def update_pcd(self, file_bytes: bytes) -> int:
+        """Locator::update fed from a PCD v0.7 file image parsed on the device; returns the point count."""
+        n = C.c_int()
+        _lib.check(self._lib.rmr_locator_update_pcd(self._h, file_bytes, len(file_bytes), C.byref(n)))
+        return n.value
+
     def update_device(self, dev_ptr: int, n_points: int, stride_bytes: int):
         _lib.check(self._lib.rmr_locator_update_device(self._h, C.c_void_p(dev_ptr), n_points, stride_bytes))
 
@@ -400,6 +406,15 @@ def run_once(detector: "RobotDetector", locator: "Locator", image: np.ndarray, c
     recs, n = run_once_records(detector, locator, img.ctypes.data, False, img.shape[1], img.shape[0], img.strides[0],
                                pts.ctypes.data if pts is not None else 0, False, len(pts) if pts is not None else 0, 12)
     return [_robot_from_rec(recs[i]) for i in range(n)]
+
+
+def pcd_parse(file_bytes: bytes, capacity: int = 1 << 21, device: int = 0) -> np.ndarray:
+    """PCD v0.7 file image -> [n, 3] float32, parsed on the device (pcl::io::loadPCDFile stand-in)."""
+    lib = _lib.load()
+    out = np.empty((capacity, 3), np.float32)
+    n = C.c_int()
+    _lib.check(lib.rmr_pcd_parse(file_bytes, len(file_bytes), out.ctypes.data, capacity, C.byref(n), device))
+    return out[:n.value].copy()
 
 
 def conv_selftest(n, h, w, cin, cout, k, stride, act=1, residual=0, out_f32=0, seed=0, iters=0):

@@ -37,7 +37,7 @@ SYMBOLS = [
     "rmr_robot_detector_set_stream", "rmr_robot_detector_last_stats", "rmr_robot_detector_car",
     "rmr_robot_detector_armor",
     "rmr_locator_create", "rmr_locator_destroy", "rmr_locator_update", "rmr_locator_update_device",
-    "rmr_locator_cluster", "rmr_locator_search", "rmr_locator_load_background", "rmr_locator_set_stream", "rmr_locator_image_size",
+    "rmr_locator_cluster", "rmr_locator_search", "rmr_locator_update_pcd", "rmr_pcd_parse", "rmr_locator_load_background", "rmr_locator_set_stream", "rmr_locator_image_size",
     "rmr_locator_read_image", "rmr_locator_stats", "rmr_locator_read_foreground",
     "rmr_run_once", "rmr_conv_selftest", "rmr_conv_timeline",
 ]
@@ -95,6 +95,8 @@ def load():
     lib.rmr_locator_update_device.argtypes = [vp, vp, ci, ci]
     lib.rmr_locator_cluster.argtypes = [vp]
     lib.rmr_locator_search.argtypes = [vp, P(RobotRec), ci]
+    lib.rmr_locator_update_pcd.argtypes = [vp, vp, C.c_size_t, P(ci)]
+    lib.rmr_pcd_parse.argtypes = [vp, C.c_size_t, vp, ci, P(ci), ci]
     lib.rmr_locator_load_background.argtypes = [vp, vp, ci, ci]
     lib.rmr_locator_set_stream.argtypes = [vp, vp]
     lib.rmr_locator_image_size.argtypes = [vp, P(ci), P(ci)]

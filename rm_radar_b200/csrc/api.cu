@@ -7,6 +7,7 @@
 #include "../../include/rm_radar_b200.h"
 #include "detector.h"
 #include "locate.h"
+#include "pcd.h"
 
 using namespace rmr;
 
@@ -21,6 +22,7 @@ struct rmr_robot_detector {
 };
 struct rmr_locator {
     std::unique_ptr<Locator> impl;
+    std::unique_ptr<PcdParser> pcd;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     int device = 0;
 };
@@ -275,6 +277,7 @@ void rmr_locator_destroy(rmr_locator_t* l) {
     cudaSetDevice(l->device);
     if (l->own_stream) {
         cudaStreamSynchronize(l->own_stream);
+        l->pcd.reset();
         l->impl.reset();
         cudaStreamDestroy(l->own_stream);
     }
@@ -318,6 +321,41 @@ int rmr_locator_search(rmr_locator_t* l, rmr_robot_t* robots, int n_robots) {
             robots[i].cluster = res[i].cluster;
             robots[i].cluster_points = res[i].npoints;
         }
+    });
+}
+int rmr_locator_update_pcd(rmr_locator_t* l, const void* file_bytes, size_t size, int* n_points) {
+    return guarded([&] {
+        if (!l) throw std::invalid_argument("null argument");
+        RMR_CUDA(cudaSetDevice(l->device));
+        if (!l->pcd) l->pcd = std::make_unique<PcdParser>();
+        const int n = l->pcd->parse(file_bytes, size, l->impl->cloud_buffer(), l->impl->max_points(), l->stream);
+        if (n_points) *n_points = n;
+        l->impl->update_device(n > 0 ? l->impl->cloud_buffer() : nullptr, n, 3, l->stream);
+    });
+}
+int rmr_pcd_parse(const void* file_bytes, size_t size, float* xyz, int capacity, int* n_points, int device) {
+    return guarded([&] {
+        if (!xyz || !n_points) throw std::invalid_argument("null argument");
+        RMR_CUDA(cudaSetDevice(device));
+        const PcdHeader h = pcd_parse_header(file_bytes, size);
+        if (h.n_points > capacity) throw std::invalid_argument("PCD: more points than `capacity`");
+        PcdParser parser;
+        float* dev = nullptr;
+        RMR_CUDA(cudaMalloc(&dev, sizeof(float) * 3 * std::max<long>(h.n_points, 1)));
+        cudaStream_t s;
+        RMR_CUDA(cudaStreamCreate(&s));
+        try {
+            const int n = parser.parse(file_bytes, size, dev, capacity, s);
+            RMR_CUDA(cudaMemcpyAsync(xyz, dev, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, s));
+            RMR_CUDA(cudaStreamSynchronize(s));
+            *n_points = n;
+        } catch (...) {
+            cudaStreamDestroy(s);
+            cudaFree(dev);
+            throw;
+        }
+        cudaStreamDestroy(s);
+        cudaFree(dev);
     });
 }
 int rmr_locator_load_background(rmr_locator_t* l, const float* image, int width, int height) {

@@ -63,6 +63,8 @@ public:
     const float* depth_image() const;
     const float* background_image() const { return bg_; }
     float* background_image_mut() { return bg_; }
+    float* cloud_buffer() { return cloud_; }   // device staging for host / file clouds: [max_points][4] floats
+    int max_points() const { return max_points_; }
     const float* diff_image() const { return diff_; }
     const int* label_image() const { return label_img_; }
     const float* fg_points() const { return fg_pts_; }

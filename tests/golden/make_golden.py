@@ -67,5 +67,43 @@ def main():
     np.savez_compressed(os.path.join(HERE, "expected.npz"), **out)
 
 
+def make_pcd_fixtures():
+    """tests/golden/pcd/: a 1500-point prefix of assets/clouds/0.pcd (ASCII), an ASCII file exercising the number
+    grammar (decimals, exponents, signs, CRLF, an extra column, nan / inf, missing final newline) and a binary file
+    whose 16-byte records carry a leading intensity field."""
+    out_dir = os.path.join(HERE, "pcd")
+    os.makedirs(out_dir, exist_ok=True)
+    lines = open(f"{REF}/assets/clouds/0.pcd", "rb").read().split(b"\n")
+    hdr_end = [i for i, ln in enumerate(lines) if ln.startswith(b"DATA")][0]
+    n = 1500
+    hdr = [(b"WIDTH %d" % n if ln.startswith(b"WIDTH") else b"POINTS %d" % n if ln.startswith(b"POINTS") else ln)
+           for ln in lines[:hdr_end + 1]]
+    open(os.path.join(out_dir, "asset0_head1500_ascii.pcd"), "wb").write(
+        b"\n".join(hdr + lines[hdr_end + 1:hdr_end + 1 + n]) + b"\n")
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-30000, 30000, (400, 3))
+    rows = []
+    for i, (x, y, z) in enumerate(pts):
+        fmt = [("%.3f", "%.6g", "%d"), ("%e", "%.1f", "%+.4f"), ("%.9g", "%.2e", "%.0f")][i % 3]
+        rows.append(" ".join(f % (v if "%d" not in f else int(v)) for f, v in zip(fmt, (x, y, z))) + " %d" % (i % 255))
+    rows[5] = "nan 1 2 0"
+    rows[6] = "-inf 0.5 +7 1"
+    rows[7] = "  12.5\t-3e2   0004.250   9"
+    txt = ("# .PCD v0.7 - Point Cloud Data file format\r\nVERSION 0.7\r\nFIELDS x y z intensity\r\nSIZE 4 4 4 4\r\n"
+           "TYPE F F F U\r\nCOUNT 1 1 1 1\r\nWIDTH 400\r\nHEIGHT 1\r\nVIEWPOINT 0 0 0 1 0 0 0\r\nPOINTS 400\r\n"
+           "DATA ascii\r\n" + "\r\n".join(rows))
+    open(os.path.join(out_dir, "variants_crlf_ascii.pcd"), "wb").write(txt.encode())
+    n = 1000
+    xyz = rng.uniform(-30000, 30000, (n, 3)).astype("<f4")
+    rec = np.zeros(n, dtype=[("intensity", "<u4"), ("x", "<f4"), ("y", "<f4"), ("z", "<f4")])
+    rec["intensity"] = np.arange(n)
+    rec["x"], rec["y"], rec["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS intensity x y z\nSIZE 4 4 4 4\nTYPE U F F F\n"
+           "COUNT 1 1 1 1\nWIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary\n" % (n, n))
+    open(os.path.join(out_dir, "ixyz_binary.pcd"), "wb").write(hdr.encode() + rec.tobytes())
+    np.save(os.path.join(out_dir, "ixyz_binary_expected.npy"), xyz)
+
+
 if __name__ == "__main__":
     main()
+    make_pcd_fixtures()

@@ -101,3 +101,13 @@ def test_cluster_order_and_size_filter():
     # unclustered (-1) group competes and wins on ties by lowest id (locate.cpp:303-306)
     xyz, info = loc.search_rect((8, 88, 12, 70))   # covers the 8-run (-1), the singleton (-1), cluster 2
     assert info["cluster"] == -1 and info["n"] == 9
+
+
+def test_committed_pcd_prefix_matches_reference_asset():
+    """tests/golden/pcd/asset0_head1500_ascii.pcd is the first 1500 points of the reference's assets/clouds/0.pcd."""
+    import os
+    from tests.conftest import GOLDEN, REFERENCE, has_reference
+    a = lo.read_pcd(os.path.join(GOLDEN, "pcd", "asset0_head1500_ascii.pcd"))
+    assert a.shape == (1500, 3) and a.dtype == np.float32
+    if has_reference():
+        assert np.array_equal(a, lo.read_pcd(os.path.join(REFERENCE, "assets", "clouds", "0.pcd"))[:1500])
