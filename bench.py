@@ -263,6 +263,7 @@ def run_ours(args, rank, world, local_rank):
         for i in range(warmup):
             fn(i)
         if world > 1:
+            jobs.join()      # collectives keep one order on every rank: no all-gather may trail the barrier
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
