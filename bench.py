@@ -243,12 +243,16 @@ def run_ours(args, rank, world, local_rank):
             return
         jobs.put((rec_array_t.from_buffer_copy(recs), n))
 
+    conv_acc = [0.0, 0.0, 0]
+
     def step_resident(i):
         j = i % POOL
         loc_stream.wait_stream(stream)      # the cloud of step i is not touched before step i-1 is done
         recs, n = rr.run_once_records(det, loc, frames_dev[j].data_ptr(), True, W, H, W * 3,
                                       clouds_dev[j].data_ptr(), True, NPTS, 12)
         publish(recs, n)
+        t = det.last_timing()               # CUDA events around the two network replays of this step
+        conv_acc[0] += t[0]; conv_acc[1] += t[1]; conv_acc[2] += 1
         return n
 
     def step_e2e(i):
@@ -267,6 +271,7 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        conv_acc[:] = [0.0, 0.0, 0]          # per-step network replay times of the timed steps only
         e0.record(stream)
         n = 0
         for i in range(steps):
@@ -288,15 +293,19 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     ms_res, n_robots = timed(step_resident, args.steps, warmup)
+    car_ms_in = conv_acc[0] / max(conv_acc[2], 1)
+    armor_ms_in = conv_acc[1] / max(conv_acc[2], 1)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, args.steps, warmup)
     stats = det.last_stats()
     k_cars = stats["n_cars"]
 
     # dominant kernel: conv_umma_kernel (the two captured network graphs), timed alone on its stream
+    # (a) inside the timed region: events on the detector's stream around each replay (armor overlaps the locator);
+    # (b) the same graphs replayed alone, back to back (warm L2) -- reported beside it
     car_ms = det.car_detector().time_forward(1, 20)
     armor_ms = det.armor_detector().time_forward(max(k_cars, 1), 20) if k_cars else 0.0
-    conv_ms = car_ms + armor_ms
+    conv_ms = car_ms_in + armor_ms_in
     conv_launches = det.car_detector().plan_stats(1)["umma_convs"] + (det.armor_detector().plan_stats(k_cars)["umma_convs"] if k_cars else 0)
     peak_tf, peak_hbm, peak_src = peaks()
     achieved_tf = stats["conv_flops"] / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
@@ -326,7 +335,9 @@ def run_ours(args, rank, world, local_rank):
                      "flops_per_launch": stats["conv_flops"] / max(conv_launches, 1),
                      "avg_launch_us": 1e3 * conv_ms / max(conv_launches, 1),
                      "traffic_note": "mean dram__bytes_read+write per launch, ncu --set full, profiles/r1_conv_full.json",
-                     "car_net_ms": car_ms, "armor_net_ms": armor_ms, "armor_batch": k_cars,
+                     "car_net_ms": car_ms_in, "armor_net_ms": armor_ms_in, "armor_batch": k_cars,
+                     "timing": "CUDA events on the detector stream around each graph replay, mean over the timed steps",
+                     "replayed_alone_ms": {"car": car_ms, "armor": armor_ms},
                      "conv_share_of_step": conv_ms / (ms_res / args.steps),
                      "frac_of_conv_bound_frames_per_s": (value / world) / (peak_tf * 1e12 / stats["conv_flops"])},
         "robots_per_frame": n_robots,

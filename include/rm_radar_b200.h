@@ -114,6 +114,8 @@ int rmr_robot_detector_last_armors(rmr_robot_detector_t* d, int car_index, rmr_d
 int rmr_robot_detector_set_stream(rmr_robot_detector_t* d, void* cuda_stream);
 /* kernels launched and conv FLOPs executed by the last detect call (bench accounting) */
 int rmr_robot_detector_last_stats(rmr_robot_detector_t* d, int* kernel_launches, double* conv_flops, int* n_cars);
+/* device time of the two network replays of the last detect call (CUDA events on the detector's stream) */
+int rmr_robot_detector_last_timing(rmr_robot_detector_t* d, float* car_forward_ms, float* armor_forward_ms);
 rmr_detector_t* rmr_robot_detector_car(rmr_robot_detector_t* d);
 rmr_detector_t* rmr_robot_detector_armor(rmr_robot_detector_t* d);
 

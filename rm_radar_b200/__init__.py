@@ -279,6 +279,12 @@ class RobotDetector:
         _lib.check(self._lib.rmr_robot_detector_last_stats(self._h, C.byref(k), C.byref(f), C.byref(c)))
         return dict(kernel_launches=k.value, conv_flops=f.value, n_cars=c.value)
 
+    def last_timing(self):
+        """Device ms of the car / armor network replays of the last detect call."""
+        a, b = C.c_float(), C.c_float()
+        _lib.check(self._lib.rmr_robot_detector_last_timing(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def car_detector(self):
         return _DetectorView(self._lib, self._lib.rmr_robot_detector_car(self._h), 1, self.input_size)
 

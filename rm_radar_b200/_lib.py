@@ -34,7 +34,7 @@ SYMBOLS = [
     "rmr_detector_time_forward", "rmr_detector_profile_ops", "rmr_detector_plan_stats",
     "rmr_robot_detector_create", "rmr_robot_detector_destroy", "rmr_robot_detector_detect",
     "rmr_robot_detector_detect_device", "rmr_robot_detector_last_cars", "rmr_robot_detector_last_armors",
-    "rmr_robot_detector_set_stream", "rmr_robot_detector_last_stats", "rmr_robot_detector_car",
+    "rmr_robot_detector_set_stream", "rmr_robot_detector_last_stats", "rmr_robot_detector_last_timing", "rmr_robot_detector_car",
     "rmr_robot_detector_armor",
     "rmr_locator_create", "rmr_locator_destroy", "rmr_locator_update", "rmr_locator_update_device",
     "rmr_locator_cluster", "rmr_locator_search", "rmr_locator_update_pcd", "rmr_pcd_parse", "rmr_locator_load_background", "rmr_locator_set_stream", "rmr_locator_image_size",
@@ -84,6 +84,7 @@ def load():
     lib.rmr_robot_detector_last_armors.argtypes = [vp, ci, P(Detection), ci, P(ci)]
     lib.rmr_robot_detector_set_stream.argtypes = [vp, vp]
     lib.rmr_robot_detector_last_stats.argtypes = [vp, P(ci), P(cd), P(ci)]
+    lib.rmr_robot_detector_last_timing.argtypes = [vp, P(cf), P(cf)]
     lib.rmr_robot_detector_car.argtypes = [vp]
     lib.rmr_robot_detector_car.restype = vp
     lib.rmr_robot_detector_armor.argtypes = [vp]

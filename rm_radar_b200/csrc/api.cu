@@ -242,6 +242,13 @@ int rmr_robot_detector_last_stats(rmr_robot_detector_t* d, int* kernel_launches,
         if (n_cars) *n_cars = static_cast<int>(d->impl->last_cars().size());
     });
 }
+int rmr_robot_detector_last_timing(rmr_robot_detector_t* d, float* car_forward_ms, float* armor_forward_ms) {
+    return guarded([&] {
+        if (!d) throw std::invalid_argument("null argument");
+        if (car_forward_ms) *car_forward_ms = d->impl->last_car_ms();
+        if (armor_forward_ms) *armor_forward_ms = d->impl->last_armor_ms();
+    });
+}
 rmr_detector_t* rmr_robot_detector_car(rmr_robot_detector_t* d) { return &d->car_view; }
 rmr_detector_t* rmr_robot_detector_armor(rmr_robot_detector_t* d) { return &d->armor_view; }
 

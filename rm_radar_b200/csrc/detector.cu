@@ -88,6 +88,8 @@ Detector::Detector(const std::string& engine_path, int classes, int image_w, int
     RMR_CUDA(cudaMallocHost(&pinned_geoms_, sizeof(LetterboxGeom) * max_batch));
     RMR_CUDA(cudaMallocHost(&pinned_out_, sizeof(Detection) * kMaxOut * max_batch));
     RMR_CUDA(cudaMallocHost(&pinned_counts_, sizeof(int) * max_batch));
+    RMR_CUDA(cudaEventCreate(&ev_fwd0_));
+    RMR_CUDA(cudaEventCreate(&ev_fwd1_));
     frame_buffer(static_cast<size_t>(image_w) * image_h * 3);
     conv_init();
 }
@@ -96,6 +98,8 @@ Detector::~Detector() {
     cudaSetDevice(device_);
     if (own_stream_) cudaStreamSynchronize(own_stream_);
     post_free(post_);
+    if (ev_fwd0_) cudaEventDestroy(ev_fwd0_);
+    if (ev_fwd1_) cudaEventDestroy(ev_fwd1_);
     cudaFree(staging_); cudaFree(dev_geoms_); cudaFree(dev_frame_);
     cudaFreeHost(pinned_geoms_); cudaFreeHost(pinned_out_); cudaFreeHost(pinned_counts_); cudaFreeHost(pinned_frame_);
     net_.reset();
@@ -137,7 +141,9 @@ void Detector::enqueue(const uint8_t* dev_frame, int stride, const Roi* rois, in
     RMR_CUDA(cudaMemcpyAsync(dev_geoms_, pinned_geoms_, sizeof(LetterboxGeom) * n, cudaMemcpyHostToDevice, stream_));
     launch_letterbox(dev_frame, stride, dev_geoms_, any_unclean, any_clean, n, staging_, net_->input(), input_w_,
                      input_h_, stream_);
+    RMR_CUDA(cudaEventRecord(ev_fwd0_, stream_));
     net_->forward(n, stream_);
+    RMR_CUDA(cudaEventRecord(ev_fwd1_, stream_));
     launch_postprocess(net_->levels(), classes_, n, dev_geoms_, conf_thresh_, nms_thresh_, post_, stream_);
     RMR_CUDA(cudaMemcpyAsync(pinned_counts_, post_.out_count, sizeof(int) * n, cudaMemcpyDeviceToHost, stream_));
     RMR_CUDA(cudaMemcpyAsync(pinned_out_, post_.out, sizeof(Detection) * kMaxOut * n, cudaMemcpyDeviceToHost, stream_));
@@ -154,6 +160,7 @@ std::vector<std::vector<Detection>> Detector::collect() {
     if (n == 0) return results;
     RMR_CUDA(cudaSetDevice(device_));
     RMR_CUDA(cudaStreamSynchronize(stream_));
+    RMR_CUDA(cudaEventElapsedTime(&last_forward_ms_, ev_fwd0_, ev_fwd1_));
     for (int i = 0; i < n; ++i) {
         const int c = std::min(pinned_counts_[i], kMaxOut);
         results[i].assign(pinned_out_ + static_cast<size_t>(i) * kMaxOut, pinned_out_ + static_cast<size_t>(i) * kMaxOut + c);
@@ -346,6 +353,8 @@ std::vector<RobotRecord> RobotDetector::finish() {
     std::vector<Detection> cars = car_->collect()[0];
     last_launches_ = car_->last_launches();
     last_flops_ = car_->net().flops_per_image();
+    last_car_ms_ = car_->last_forward_ms();
+    last_armor_ms_ = 0.f;
     // Appendix B#8: more cars than max_batch_size is UB in the reference; keep the first max_cars
     if (static_cast<int>(cars.size()) > max_cars_) cars.resize(max_cars_);
     // cv::Rect(float, float, float, float): truncation (detector.cpp:420-421); ROIs are read from the
@@ -363,6 +372,7 @@ std::vector<RobotRecord> RobotDetector::finish() {
     if (!rois.empty()) {
         armor_batch = armor_->detect_device_rois(dev_bgr, stride, rois.data(), static_cast<int>(rois.size()));
         last_launches_ += armor_->last_launches();
+        last_armor_ms_ = armor_->last_forward_ms();
         last_flops_ += armor_->net().flops_per_image() * rois.size();
     }
     last_cars_ = cars;

@@ -43,6 +43,8 @@ public:
     int device() const { return device_; }
     uint8_t* frame_buffer(size_t bytes);   // device staging for host frames (grows on demand)
     int last_launches() const { return last_launches_; }
+    // device time of the last call's network replay (CUDA events on the detector's stream around Net::forward)
+    float last_forward_ms() const { return last_forward_ms_; }
 
 private:
     std::vector<std::vector<Detection>> run(const uint8_t* dev_frame, int stride, const Roi* rois, int n);
@@ -63,6 +65,8 @@ private:
     Detection* pinned_out_ = nullptr;
     int* pinned_counts_ = nullptr;
     int last_launches_ = 0;
+    cudaEvent_t ev_fwd0_ = nullptr, ev_fwd1_ = nullptr;
+    float last_forward_ms_ = 0.f;
 };
 
 struct RobotRecord {
@@ -90,6 +94,8 @@ public:
     const std::vector<std::vector<Detection>>& last_armors() const { return last_armors_; }
     int last_launches() const { return last_launches_; }
     double last_flops() const { return last_flops_; }
+    float last_car_ms() const { return last_car_ms_; }
+    float last_armor_ms() const { return last_armor_ms_; }
 
 private:
     std::unique_ptr<Detector> car_, armor_;
@@ -99,6 +105,7 @@ private:
     std::vector<std::vector<Detection>> last_armors_;
     int last_launches_ = 0;
     double last_flops_ = 0;
+    float last_car_ms_ = 0.f, last_armor_ms_ = 0.f;
     const uint8_t* cur_frame_ = nullptr;
     int cur_w_ = 0, cur_h_ = 0, cur_stride_ = 0;
 };

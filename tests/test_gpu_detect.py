@@ -108,6 +108,9 @@ def test_cascade_golden_frames(robot_detector):
         # output order: undetected robots in car order, then labelled ascending (detector.cpp:431-453)
         det_flags = [r.isDetected() for r in robots]
         assert det_flags == sorted(det_flags) and labels == sorted(labels)
+        # the event timing bench.py's roofline uses: both replays ran on the device for this call
+        car_ms, armor_ms = robot_detector.last_timing()
+        assert 0.05 < car_ms < 50 and (armor_ms > 0.05) == (len(cars) > 0)
 
 
 @needs_models
