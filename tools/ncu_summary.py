@@ -34,7 +34,7 @@ WANT = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "lau
         "launch__occupancy_limit_shared_mem", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
 UNIT = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
 
@@ -69,7 +69,7 @@ def full(path, out_json, out_md):
                 r.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0),
                 r.get("sm__throughput.avg.pct_of_peak_sustained_elapsed", 0),
                 r.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", 0),
-                (r.get("dram__bytes_read.sum", 0) + r.get("dram__bytes_write.sum", 0)) / 1e6, r.get("lts__t_bytes.sum", 0) / 1e6))
+                (r.get("dram__bytes_read.sum", 0) + r.get("dram__bytes_write.sum", 0)) / 1e6, r.get("lts__t_sectors.sum", 0) * 32 / 1e6))
     print(open(out_md).read())
 
 
