@@ -3,6 +3,9 @@ Run in the build container (needs /root/reference):   python tests/golden/make_g
   frames/0.jpg, frames/5.jpg   verbatim copies of assets/images (input data, not source)
   clouds.npz                    assets/clouds 0..3 + every 4th point of background.pcd
   expected.npz                  oracle outputs (fp32 ONNX via oracle/onnx_torch.py, compat letterbox)
+  jpeg/*.jpg, jpeg/expected.npz what cv2.imdecode (= the reference's cv::imread) returns for small synthetic files
+                                (4:4:4 / 4:2:2 / 4:2:0 / grayscale, restart intervals, optimised tables, odd sizes)
+                                and sha256 of the decoded reference frames 0 and 5
 """
 import os
 import shutil
@@ -19,6 +22,42 @@ from oracle import detect_oracle as do  # noqa: E402
 from oracle import locate_oracle as lo  # noqa: E402
 from oracle.onnx_torch import OnnxNet  # noqa: E402
 from tests import fixtures as fx  # noqa: E402
+
+
+def make_jpeg_fixtures():
+    """Golden vectors for the JPEG stage: outputs of cv2.imdecode, the call the reference makes (samples/main.cpp:24-40)."""
+    import hashlib
+
+    import cv2
+    d = os.path.join(HERE, "jpeg")
+    os.makedirs(d, exist_ok=True)
+    src = cv2.imread(os.path.join(HERE, "frames", "0.jpg"), cv2.IMREAD_COLOR)
+    rng = np.random.default_rng(7)
+    S = {"444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+         "420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420}
+    cases = [("photo_420_q90", (97, 61), "420", 90, 0, 0, False), ("photo_444_q75_opt", (97, 61), "444", 75, 0, 1, False),
+             ("photo_422_q50_rst3", (130, 47), "422", 50, 3, 0, False), ("photo_420_q95_rst1_opt", (64, 48), "420", 95, 1, 1, False),
+             ("noise_420_q100", (33, 17), "420", 100, 0, 0, True), ("noise_444_q30_rst2", (40, 24), "444", 30, 2, 0, True),
+             ("tiny_420", (3, 2), "420", 90, 0, 0, False), ("gray_q80", (75, 50), None, 80, 0, 0, False)]
+    out = {}
+    for name, (w, h), samp, q, rst, opt, noise in cases:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if noise else \
+            cv2.resize(src[500:1500, 800:2200], (w, h), interpolation=cv2.INTER_AREA)
+        flags = [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_RST_INTERVAL, rst, cv2.IMWRITE_JPEG_OPTIMIZE, opt]
+        if samp is None:
+            img = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+        else:
+            flags += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, S[samp]]
+        ok, enc = cv2.imencode(".jpg", img, flags)
+        assert ok
+        open(os.path.join(d, name + ".jpg"), "wb").write(enc.tobytes())
+        out[name] = cv2.imdecode(enc, cv2.IMREAD_COLOR)
+    for i in (0, 5):
+        img = cv2.imread(os.path.join(HERE, "frames", f"{i}.jpg"), cv2.IMREAD_COLOR)
+        out[f"frame{i}_sha256"] = np.frombuffer(hashlib.sha256(img.tobytes()).digest(), np.uint8)
+        out[f"frame{i}_shape"] = np.asarray(img.shape, np.int32)
+    np.savez_compressed(os.path.join(d, "expected.npz"), **out)
+    print("jpeg fixtures:", sorted(out))
 
 
 def main():
@@ -105,5 +144,8 @@ def make_pcd_fixtures():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "jpeg":
+        make_jpeg_fixtures()
+        sys.exit(0)
     main()
     make_pcd_fixtures()
