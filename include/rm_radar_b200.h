@@ -141,6 +141,37 @@ int rmr_locator_search(rmr_locator_t* l, rmr_robot_t* robots, int n_robots);
 int rmr_locator_update_pcd(rmr_locator_t* l, const void* file_bytes, size_t size, int* n_points);
 /* the same parser with the points copied back (tests, tools): xyz = float [capacity][3] on the host */
 int rmr_pcd_parse(const void* file_bytes, size_t size, float* xyz, int capacity, int* n_points, int device);
+/* ---- JPEG frames ----
+ * Replaces cv::imread in front of RobotDetector::detect (samples/main.cpp:24-40): the file image is uploaded as it
+ * is (~1/16 of the raw frame) and decoded on the device into the BGR frame the detector reads.  Baseline / extended
+ * sequential Huffman JPEG, 8 bit, grayscale or YCbCr 4:4:4 / 4:2:2 / 4:2:0, with or without restart markers;
+ * anything else fails with RMR_ERR_INVALID_ARGUMENT.  Output is bit-identical to libjpeg-turbo's default decode
+ * (JDCT_ISLOW, fancy upsampling), i.e. to what cv::imread returns. */
+typedef struct rmr_jpeg_decoder rmr_jpeg_decoder_t;
+int rmr_jpeg_decoder_create(rmr_jpeg_decoder_t** out, int device);
+void rmr_jpeg_decoder_destroy(rmr_jpeg_decoder_t* dec);
+int rmr_jpeg_decoder_set_stream(rmr_jpeg_decoder_t* dec, void* cuda_stream);
+/* header fields without touching the device */
+int rmr_jpeg_info(const void* file_bytes, size_t size, int* width, int* height, int* components, int* h_samp,
+                  int* v_samp, int* restart_interval);
+/* cv::imread: decode into a host buffer of `capacity` >= width * height * 3 bytes (BGR, packed rows) */
+int rmr_jpeg_decode(rmr_jpeg_decoder_t* dec, const void* file_bytes, size_t size, uint8_t* bgr, size_t capacity,
+                    int* width, int* height);
+/* decode into device memory, asynchronously on the decoder's stream: `dev_bgr` (row pitch `stride_bytes`) or, when
+ * dev_bgr is NULL, the decoder's own frame buffer (pitch width * 3), returned through `frame`. */
+int rmr_jpeg_decode_device(rmr_jpeg_decoder_t* dec, const void* file_bytes, size_t size, void* dev_bgr,
+                           int stride_bytes, const void** frame, int* width, int* height);
+/* waits for the last decode; *status = 0 when the entropy-coded data decoded cleanly */
+int rmr_jpeg_decoder_status(rmr_jpeg_decoder_t* dec, int* status, int* sync_rounds, int* kernel_launches,
+                            size_t* upload_bytes);
+/* profiling aid: device ms of the 7 stages of one decode (upload, clear, unstuff, entropy, DC scan, IDCT, colour) */
+int rmr_jpeg_decoder_profile(rmr_jpeg_decoder_t* dec, const void* file_bytes, size_t size, float* stage_ms7);
+/* test hook: quantised coefficient blocks of the last decode, int16 [n_blocks][64], scan order x natural order */
+int rmr_jpeg_decoder_read_coefficients(rmr_jpeg_decoder_t* dec, int16_t* out, long capacity_blocks, long* n_blocks);
+/* cv::imread + RobotDetector::detect without the raw frame ever crossing PCIe: decode on the decoder's stream,
+ * detect on the detector's stream behind an event */
+int rmr_robot_detector_detect_jpeg(rmr_robot_detector_t* d, rmr_jpeg_decoder_t* dec, const void* file_bytes,
+                                   size_t size, rmr_robot_t* out, int capacity, int* count);
 /* background persistence: the running-max background depth image (locate.cpp:188-191) is the
  * only long-lived Locator state; the reference re-derives it from background.pcd at every start
  * (samples/README.md:3).  save = rmr_locator_read_image(l, 1, out); load replaces it (float [Hz][Wz], zoomed size). */

@@ -255,6 +255,14 @@ class RobotDetector:
                                                        img.strides[0], self._recs, self.max_cars, C.byref(n)))
         return [_robot_from_rec(self._recs[i]) for i in range(min(n.value, self.max_cars))]
 
+    def detect_jpeg(self, decoder: "JpegDecoder", file_bytes: bytes) -> list:
+        """cv::imread + RobotDetector::detect (samples/main.cpp:24-40, detector.cpp:413-455): the JPEG is decoded on the
+        device and the frame never crosses PCIe."""
+        n = C.c_int()
+        _lib.check(self._lib.rmr_robot_detector_detect_jpeg(self._h, decoder._h, file_bytes, len(file_bytes), self._recs,
+                                                            self.max_cars, C.byref(n)))
+        return [_robot_from_rec(self._recs[i]) for i in range(min(n.value, self.max_cars))]
+
     def detect_records(self, ptr: int, width: int, height: int, stride: int, device_ptr: bool):
         """Raw-record variant used by the bench: returns (ctypes RobotRec array, count)."""
         n = C.c_int()
@@ -412,6 +420,66 @@ def run_once(detector: "RobotDetector", locator: "Locator", image: np.ndarray, c
     recs, n = run_once_records(detector, locator, img.ctypes.data, False, img.shape[1], img.shape[0], img.strides[0],
                                pts.ctypes.data if pts is not None else 0, False, len(pts) if pts is not None else 0, 12)
     return [_robot_from_rec(recs[i]) for i in range(n)]
+
+
+def jpeg_info(file_bytes: bytes) -> dict:
+    """Header fields of a JPEG file image (host only)."""
+    lib = _lib.load()
+    v = [C.c_int() for _ in range(6)]
+    _lib.check(lib.rmr_jpeg_info(file_bytes, len(file_bytes), *[C.byref(x) for x in v]))
+    return dict(zip(("width", "height", "components", "h_samp", "v_samp", "restart_interval"), (x.value for x in v)))
+
+
+class JpegDecoder:
+    """Device-side cv::imread for baseline JPEG (samples/main.cpp:24-40); bit-exact with libjpeg-turbo's defaults."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        _lib.check(self._lib.rmr_jpeg_decoder_create(C.byref(self._h), device))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.rmr_jpeg_decoder_destroy(self._h)
+            self._h.value = None
+
+    def set_stream(self, cuda_stream: int):
+        _lib.check(self._lib.rmr_jpeg_decoder_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def decode(self, file_bytes: bytes) -> np.ndarray:
+        """-> BGR uint8 [H, W, 3] on the host (what cv2.imdecode / cv::imread returns)."""
+        meta = jpeg_info(file_bytes)
+        out = np.empty((meta["height"], meta["width"], 3), np.uint8)
+        w, h = C.c_int(), C.c_int()
+        _lib.check(self._lib.rmr_jpeg_decode(self._h, file_bytes, len(file_bytes), out.ctypes.data, out.nbytes,
+                                             C.byref(w), C.byref(h)))
+        return out
+
+    def decode_device(self, file_bytes: bytes, dev_ptr: int = 0, stride: int = 0):
+        """Asynchronous decode into device memory; returns (device pointer, width, height)."""
+        frame = C.c_void_p()
+        w, h = C.c_int(), C.c_int()
+        _lib.check(self._lib.rmr_jpeg_decode_device(self._h, file_bytes, len(file_bytes), C.c_void_p(dev_ptr or None),
+                                                    stride, C.byref(frame), C.byref(w), C.byref(h)))
+        return frame.value, w.value, h.value
+
+    def status(self) -> dict:
+        st, rounds, launches, up = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        _lib.check(self._lib.rmr_jpeg_decoder_status(self._h, C.byref(st), C.byref(rounds), C.byref(launches), C.byref(up)))
+        return dict(status=st.value, sync_rounds=rounds.value, kernel_launches=launches.value, upload_bytes=up.value)
+
+    def profile(self, file_bytes: bytes) -> dict:
+        """Device ms per stage of one decode (CUDA events between the launches)."""
+        ms = (C.c_float * 7)()
+        _lib.check(self._lib.rmr_jpeg_decoder_profile(self._h, file_bytes, len(file_bytes), ms))
+        return dict(zip(("upload", "clear", "unstuff", "entropy", "dc_scan", "idct", "colour"), (float(x) for x in ms)))
+
+    def coefficients(self, n_blocks: int) -> np.ndarray:
+        """Quantised coefficient blocks of the last decode, int16 [n_blocks, 64] (scan order x natural order)."""
+        out = np.empty((n_blocks, 64), np.int16)
+        n = C.c_long()
+        _lib.check(self._lib.rmr_jpeg_decoder_read_coefficients(self._h, out.ctypes.data, n_blocks, C.byref(n)))
+        return out[:n.value]
 
 
 def pcd_parse(file_bytes: bytes, capacity: int = 1 << 21, device: int = 0) -> np.ndarray:

@@ -40,6 +40,8 @@ SYMBOLS = [
     "rmr_locator_cluster", "rmr_locator_search", "rmr_locator_update_pcd", "rmr_pcd_parse", "rmr_locator_load_background", "rmr_locator_set_stream", "rmr_locator_image_size",
     "rmr_locator_read_image", "rmr_locator_stats", "rmr_locator_read_foreground",
     "rmr_run_once", "rmr_conv_selftest", "rmr_conv_timeline",
+    "rmr_jpeg_decoder_create", "rmr_jpeg_decoder_destroy", "rmr_jpeg_decoder_set_stream", "rmr_jpeg_info", "rmr_jpeg_decode",
+    "rmr_jpeg_decode_device", "rmr_jpeg_decoder_status", "rmr_jpeg_decoder_read_coefficients", "rmr_jpeg_decoder_profile", "rmr_robot_detector_detect_jpeg",
 ]
 
 _lib = None
@@ -98,6 +100,17 @@ def load():
     lib.rmr_locator_search.argtypes = [vp, P(RobotRec), ci]
     lib.rmr_locator_update_pcd.argtypes = [vp, vp, C.c_size_t, P(ci)]
     lib.rmr_pcd_parse.argtypes = [vp, C.c_size_t, vp, ci, P(ci), ci]
+    lib.rmr_jpeg_decoder_create.argtypes = [P(vp), ci]
+    lib.rmr_jpeg_decoder_destroy.argtypes = [vp]
+    lib.rmr_jpeg_decoder_destroy.restype = None
+    lib.rmr_jpeg_decoder_set_stream.argtypes = [vp, vp]
+    lib.rmr_jpeg_info.argtypes = [vp, C.c_size_t] + [P(ci)] * 6
+    lib.rmr_jpeg_decode.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, P(ci), P(ci)]
+    lib.rmr_jpeg_decode_device.argtypes = [vp, vp, C.c_size_t, vp, ci, P(vp), P(ci), P(ci)]
+    lib.rmr_jpeg_decoder_status.argtypes = [vp, P(ci), P(ci), P(ci), P(C.c_size_t)]
+    lib.rmr_jpeg_decoder_profile.argtypes = [vp, vp, C.c_size_t, P(cf)]
+    lib.rmr_jpeg_decoder_read_coefficients.argtypes = [vp, vp, C.c_long, P(C.c_long)]
+    lib.rmr_robot_detector_detect_jpeg.argtypes = [vp, vp, vp, C.c_size_t, vp, ci, P(ci)]
     lib.rmr_locator_load_background.argtypes = [vp, vp, ci, ci]
     lib.rmr_locator_set_stream.argtypes = [vp, vp]
     lib.rmr_locator_image_size.argtypes = [vp, P(ci), P(ci)]

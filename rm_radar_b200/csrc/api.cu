@@ -7,6 +7,7 @@
 #include "../../include/rm_radar_b200.h"
 #include "detector.h"
 #include "locate.h"
+#include "jpeg.h"
 #include "pcd.h"
 
 using namespace rmr;
@@ -19,6 +20,10 @@ struct rmr_robot_detector {
     std::unique_ptr<RobotDetector> impl;
     rmr_detector car_view, armor_view;
     int last_cars = 0;
+};
+struct rmr_jpeg_decoder {
+    std::unique_ptr<JpegDecoder> impl;
+    cudaEvent_t decoded = nullptr;
 };
 struct rmr_locator {
     std::unique_ptr<Locator> impl;
@@ -363,6 +368,99 @@ int rmr_pcd_parse(const void* file_bytes, size_t size, float* xyz, int capacity,
         }
         cudaStreamDestroy(s);
         cudaFree(dev);
+    });
+}
+int rmr_jpeg_decoder_create(rmr_jpeg_decoder_t** out, int device) {
+    return guarded([&] {
+        if (!out) throw std::invalid_argument("null argument");
+        auto h = std::make_unique<rmr_jpeg_decoder>();
+        h->impl = std::make_unique<JpegDecoder>(device);
+        RMR_CUDA(cudaEventCreateWithFlags(&h->decoded, cudaEventDisableTiming));
+        *out = h.release();
+    });
+}
+void rmr_jpeg_decoder_destroy(rmr_jpeg_decoder_t* dec) {
+    if (!dec) return;
+    dec->impl.reset();
+    if (dec->decoded) cudaEventDestroy(dec->decoded);
+    delete dec;
+}
+int rmr_jpeg_decoder_set_stream(rmr_jpeg_decoder_t* dec, void* cuda_stream) {
+    return guarded([&] {
+        if (!dec) throw std::invalid_argument("null argument");
+        dec->impl->set_stream(static_cast<cudaStream_t>(cuda_stream));
+    });
+}
+int rmr_jpeg_info(const void* file_bytes, size_t size, int* width, int* height, int* components, int* h_samp,
+                  int* v_samp, int* restart_interval) {
+    return guarded([&] {
+        const JpegHeader h = jpeg_parse_header(file_bytes, size);
+        if (width) *width = h.width;
+        if (height) *height = h.height;
+        if (components) *components = h.components;
+        if (h_samp) *h_samp = h.h_samp;
+        if (v_samp) *v_samp = h.v_samp;
+        if (restart_interval) *restart_interval = h.restart_interval;
+    });
+}
+int rmr_jpeg_decode(rmr_jpeg_decoder_t* dec, const void* file_bytes, size_t size, uint8_t* bgr, size_t capacity,
+                    int* width, int* height) {
+    return guarded([&] {
+        if (!dec || !file_bytes) throw std::invalid_argument("null argument");
+        dec->impl->decode_to_host(file_bytes, size, bgr, capacity, width, height);
+    });
+}
+int rmr_jpeg_decode_device(rmr_jpeg_decoder_t* dec, const void* file_bytes, size_t size, void* dev_bgr,
+                           int stride_bytes, const void** frame, int* width, int* height) {
+    return guarded([&] {
+        if (!dec || !file_bytes) throw std::invalid_argument("null argument");
+        const uint8_t* f = dec->impl->decode(file_bytes, size, static_cast<uint8_t*>(dev_bgr), stride_bytes, width, height);
+        if (frame) *frame = f;
+    });
+}
+int rmr_jpeg_decoder_status(rmr_jpeg_decoder_t* dec, int* status, int* sync_rounds, int* kernel_launches,
+                            size_t* upload_bytes) {
+    return guarded([&] {
+        if (!dec) throw std::invalid_argument("null argument");
+        const int st = dec->impl->status();
+        if (status) *status = st;
+        if (sync_rounds) *sync_rounds = dec->impl->last_rounds();
+        if (kernel_launches) *kernel_launches = dec->impl->last_launches();
+        if (upload_bytes) *upload_bytes = dec->impl->last_upload_bytes();
+    });
+}
+int rmr_jpeg_decoder_profile(rmr_jpeg_decoder_t* dec, const void* file_bytes, size_t size, float* stage_ms7) {
+    return guarded([&] {
+        if (!dec || !file_bytes || !stage_ms7) throw std::invalid_argument("null argument");
+        dec->impl->profile(file_bytes, size, stage_ms7);
+    });
+}
+int rmr_jpeg_decoder_read_coefficients(rmr_jpeg_decoder_t* dec, int16_t* out, long capacity_blocks, long* n_blocks) {
+    return guarded([&] {
+        if (!dec) throw std::invalid_argument("null argument");
+        const long n = dec->impl->read_coefficients(out, capacity_blocks);
+        if (n_blocks) *n_blocks = n;
+    });
+}
+int rmr_robot_detector_detect_jpeg(rmr_robot_detector_t* d, rmr_jpeg_decoder_t* dec, const void* file_bytes,
+                                   size_t size, rmr_robot_t* out, int capacity, int* count) {
+    if (!d || !dec || !file_bytes) return guarded([] { throw std::invalid_argument("null argument"); });
+    int w = 0, h = 0;
+    const uint8_t* frame = nullptr;
+    const int st = guarded([&] {
+        frame = dec->impl->decode(file_bytes, size, nullptr, 0, &w, &h);
+        cudaStream_t det_stream = d->impl->car().stream();
+        if (det_stream != dec->impl->stream()) {
+            RMR_CUDA(cudaEventRecord(dec->decoded, dec->impl->stream()));
+            RMR_CUDA(cudaStreamWaitEvent(det_stream, dec->decoded, 0));
+        }
+    });
+    if (st) return st;
+    const int st2 = robot_detect_common(d, frame, true, w, h, w * 3, out, capacity, count);
+    if (st2) return st2;
+    return guarded([&] {
+        const int js = dec->impl->status();
+        if (js) throw std::runtime_error("jpeg: corrupt entropy-coded data (status " + std::to_string(js) + ")");
     });
 }
 int rmr_locator_load_background(rmr_locator_t* l, const float* image, int width, int height) {
