@@ -300,6 +300,41 @@ def run_ours(args, rank, world, local_rank):
     stats = det.last_stats()
     k_cars = stats["n_cars"]
 
+    # §8f rank 1: the same step fed the way the reference is fed -- a JPEG file image (cv::imread, samples/main.cpp:24-40).
+    # The file is uploaded and decoded on the device (jpeg.cu) on the detector's stream; the cloud comes from pinned host.
+    jpeg_leg = None
+    try:
+        import cv2
+        ok, enc = cv2.imencode(".jpg", frame, [cv2.IMWRITE_JPEG_QUALITY, 95])
+        jpg = enc.tobytes()
+        dec = rr.JpegDecoder(local_rank)
+        dec.set_stream(stream.cuda_stream)
+
+        def step_jpeg(i):
+            j = i % POOL
+            loc_stream.wait_stream(stream)
+            ptr, _, _ = dec.decode_device(jpg)
+            recs, n = rr.run_once_records(det, loc, ptr, True, W, H, W * 3, clouds_pin[j].data_ptr(), False, NPTS, 12)
+            publish(recs, n)
+            return n
+
+        ms_jpeg, n_jpeg = timed(step_jpeg, args.steps, warmup)
+        st = dec.status()
+        prof = dec.profile(jpg)
+        buf = np.frombuffer(jpg, np.uint8)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            cv2.imdecode(buf, cv2.IMREAD_COLOR)
+        cv_ms = (time.perf_counter() - t0) / 10 * 1e3
+        jpeg_leg = {"value": world * args.steps / (ms_jpeg * 1e-3), "unit": "frames/s", "ms_per_step": ms_jpeg / args.steps,
+                    "h2d_bytes_per_step": int(st["upload_bytes"] + cbytes + 20 * 20 + 21 * 76), "jpeg_file_bytes": len(jpg),
+                    "raw_frame_bytes": int(fbytes), "decode_stage_ms": {k: round(v, 4) for k, v in prof.items()},
+                    "sync_rounds": st["sync_rounds"], "robots_per_frame": n_jpeg,
+                    "cv2_imdecode_ms": cv_ms, "cv2_kind": "reference (OpenCV's libjpeg-turbo, 1 host thread)",
+                    "input": "the bench frame as a 4:2:0 quality-95 JPEG (cv2.imencode)"}
+    except ImportError:
+        pass
+
     # dominant kernel: conv_umma_kernel (the two captured network graphs), timed alone on its stream
     # (a) inside the timed region: events on the detector's stream around each replay (armor overlaps the locator);
     # (b) the same graphs replayed alone, back to back (warm L2) -- reported beside it
@@ -342,6 +377,8 @@ def run_ours(args, rank, world, local_rank):
                      "frac_of_conv_bound_frames_per_s": (value / world) / (peak_tf * 1e12 / stats["conv_flops"])},
         "robots_per_frame": n_robots,
     }
+    if jpeg_leg is not None:
+        line["e2e_jpeg"] = jpeg_leg
     if world == 1 and not args.no_cpu_baseline:
         try:
             cb = cpu_path(frame, bg, cloud, fx, budget_s=20.0, max_frames=8)

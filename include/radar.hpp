@@ -269,6 +269,42 @@ class Detector {
 };
 
 // radar::RobotDetector — src/detect/detector.h:171-190, detector.cpp:377-455
+// cv::imread stand-in for baseline JPEG (samples/main.cpp:24-40): the file image is decoded on the device; the frame
+// either comes back to the host (imdecode) or stays in HBM for RobotDetector::detect(JpegDecoder&, ...).
+struct HostImage {
+    std::vector<unsigned char> data;   // BGR, packed rows
+    int width = 0, height = 0;
+    ImageView view() const { return ImageView{data.data(), width, height, width * 3}; }
+};
+class JpegDecoder {
+   public:
+    JpegDecoder(const JpegDecoder&) = delete;
+    JpegDecoder& operator=(const JpegDecoder&) = delete;
+    explicit JpegDecoder(int device = 0) { detail::throw_status(rmr_jpeg_decoder_create(&handle_, device)); }
+    ~JpegDecoder() { rmr_jpeg_decoder_destroy(handle_); }
+    // cv::imdecode(bytes, cv::IMREAD_COLOR); throws std::invalid_argument for files outside the supported subset
+    HostImage imdecode(const void* file_bytes, size_t size) {
+        HostImage out;
+        detail::throw_status(rmr_jpeg_info(file_bytes, size, &out.width, &out.height, nullptr, nullptr, nullptr, nullptr));
+        out.data.resize(static_cast<size_t>(out.width) * out.height * 3);
+        detail::throw_status(rmr_jpeg_decode(handle_, file_bytes, size, out.data.data(), out.data.size(), &out.width, &out.height));
+        return out;
+    }
+#ifdef RADAR_HPP_HAS_OPENCV
+    cv::Mat imdecode(const std::vector<unsigned char>& file) {
+        int w = 0, h = 0;
+        detail::throw_status(rmr_jpeg_info(file.data(), file.size(), &w, &h, nullptr, nullptr, nullptr, nullptr));
+        cv::Mat out(h, w, CV_8UC3);
+        detail::throw_status(rmr_jpeg_decode(handle_, file.data(), file.size(), out.data, out.total() * 3, &w, &h));
+        return out;
+    }
+#endif
+    rmr_jpeg_decoder_t* handle() const noexcept { return handle_; }
+
+   private:
+    rmr_jpeg_decoder_t* handle_ = nullptr;
+};
+
 class RobotDetector {
    public:
     RobotDetector() = delete;
@@ -299,6 +335,16 @@ class RobotDetector {
         if (rmr_robot_detector_detect(handle_, image.data, image.width, image.height, stride, records_.data(),
                                       max_cars_, &n) != RMR_OK)
             detail::fatal("RobotDetector::detect");
+        std::vector<Robot> robots;
+        robots.reserve(static_cast<size_t>(n));
+        for (int i = 0; i < n && i < max_cars_; ++i) robots.push_back(Robot::fromRecord(records_[static_cast<size_t>(i)]));
+        return robots;
+    }
+    // cv::imread + detect: the JPEG is decoded on the device and the frame never crosses PCIe
+    std::vector<Robot> detect(JpegDecoder& decoder, const void* file_bytes, size_t size) {
+        int n = 0;
+        if (rmr_robot_detector_detect_jpeg(handle_, decoder.handle(), file_bytes, size, records_.data(), max_cars_, &n) != RMR_OK)
+            detail::fatal("RobotDetector::detect(jpeg)");
         std::vector<Robot> robots;
         robots.reserve(static_cast<size_t>(n));
         for (int i = 0; i < n && i < max_cars_; ++i) robots.push_back(Robot::fromRecord(records_[static_cast<size_t>(i)]));

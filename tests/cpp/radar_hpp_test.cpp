@@ -4,6 +4,7 @@
 // compares with the oracle.  Inputs are raw files written by the test (no OpenCV / PCL needed):
 //   radar_hpp_test car.rmeng armor.rmeng frame.bgr W H background.f32 cloud.f32
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
@@ -23,8 +24,8 @@ std::vector<char> slurp(const char* path) {
 }  // namespace
 
 int main(int argc, char** argv) {
-    if (argc != 8) {
-        std::fprintf(stderr, "usage: %s car.rmeng armor.rmeng frame.bgr W H background.f32 cloud.f32\n", argv[0]);
+    if (argc != 8 && argc != 9) {
+        std::fprintf(stderr, "usage: %s car.rmeng armor.rmeng frame.bgr W H background.f32 cloud.f32 [frame.jpg]\n", argv[0]);
         return 2;
     }
     const int W = std::atoi(argv[4]), H = std::atoi(argv[5]);
@@ -72,8 +73,28 @@ int main(int argc, char** argv) {
                 run_once_same = r2[i].location()->x == robots[i].location()->x && r2[i].location()->z == robots[i].location()->z;
         }
     }
-    std::printf("{\"ctor_throws\": %s, \"run_once_same\": %s, \"robots\": [", threw ? "true" : "false",
-                run_once_same ? "true" : "false");
+    // cv::imread stand-in: frame.jpg decoded on the device must be the bytes of frame.bgr (= cv2.imread of that file),
+    // and detect(decoder, file) must give the robots of detect(frame)
+    bool jpeg_same = false, jpeg_detect_same = false, jpeg_rejects = false;
+    if (argc == 9) {
+        const std::vector<char> jpg = slurp(argv[8]);
+        radar::JpegDecoder decoder;
+        const radar::HostImage img = decoder.imdecode(jpg.data(), jpg.size());
+        jpeg_same = img.width == W && img.height == H && std::memcmp(img.data.data(), frame.data(), frame.size()) == 0;
+        const std::vector<radar::Robot> r3 = detector.detect(decoder, jpg.data(), jpg.size());
+        jpeg_detect_same = r3.size() == robots.size();
+        for (size_t i = 0; jpeg_detect_same && i < robots.size(); ++i)
+            jpeg_detect_same = r3[i].label() == robots[i].label() && r3[i].rectf()->x == robots[i].rectf()->x &&
+                               r3[i].rectf()->height == robots[i].rectf()->height;
+        try {
+            decoder.imdecode("not a jpeg", 10);
+        } catch (const std::invalid_argument&) {
+            jpeg_rejects = true;
+        }
+    }
+    std::printf("{\"ctor_throws\": %s, \"run_once_same\": %s, \"jpeg_same\": %s, \"jpeg_detect_same\": %s, \"jpeg_rejects\": %s, \"robots\": [",
+                threw ? "true" : "false", run_once_same ? "true" : "false", jpeg_same ? "true" : "false",
+                jpeg_detect_same ? "true" : "false", jpeg_rejects ? "true" : "false");
     for (size_t i = 0; i < robots.size(); ++i) {
         const radar::Robot& r = robots[i];
         const auto rf = r.rectf().value();

@@ -23,12 +23,15 @@ def test_cpp_host_run_once(tmp_path):
     (tmp_path / "bg.f32").write_bytes(np.ascontiguousarray(clouds["background"][:, :3], np.float32).tobytes())
     (tmp_path / "c0.f32").write_bytes(np.ascontiguousarray(clouds["c0"][:, :3], np.float32).tobytes())
     out = subprocess.run([BIN, fx.engine("car"), fx.engine("armor"), str(tmp_path / "frame.bgr"),
-                          str(img.shape[1]), str(img.shape[0]), str(tmp_path / "bg.f32"), str(tmp_path / "c0.f32")],
+                          str(img.shape[1]), str(img.shape[0]), str(tmp_path / "bg.f32"), str(tmp_path / "c0.f32"),
+                          os.path.join(fx.GOLDEN, "frames", "0.jpg")],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     doc = json.loads(out.stdout)
     assert doc["ctor_throws"] is True
     assert doc["run_once_same"] is True      # radar::runOnce == update + cluster + detect + search
+    assert doc["jpeg_same"] is True          # radar::JpegDecoder::imdecode == cv2.imread, byte for byte
+    assert doc["jpeg_detect_same"] is True and doc["jpeg_rejects"] is True
     robots = doc["robots"]
     rects = np.array([r["rect"] for r in robots], np.float32)
     assert len(rects) == len(exp["f0_robot_rects"])
