@@ -162,10 +162,11 @@ int rmr_jpeg_decode(rmr_jpeg_decoder_t* dec, const void* file_bytes, size_t size
 int rmr_jpeg_decode_device(rmr_jpeg_decoder_t* dec, const void* file_bytes, size_t size, void* dev_bgr,
                            int stride_bytes, const void** frame, int* width, int* height);
 /* waits for the last decode; *status = 0 when the entropy-coded data decoded cleanly */
-int rmr_jpeg_decoder_status(rmr_jpeg_decoder_t* dec, int* status, int* sync_rounds, int* kernel_launches,
-                            size_t* upload_bytes);
-/* profiling aid: device ms of the 7 stages of one decode (upload, clear, unstuff, entropy, DC scan, IDCT, colour) */
-int rmr_jpeg_decoder_profile(rmr_jpeg_decoder_t* dec, const void* file_bytes, size_t size, float* stage_ms7);
+int rmr_jpeg_decoder_status(rmr_jpeg_decoder_t* dec, int* status, int* sync_rounds, int* loop_decodes,
+                            int* kernel_launches, size_t* upload_bytes);
+/* profiling aid: device ms of the 7 stages of one decode (upload, clear, unstuff, entropy, DC scan, IDCT, colour)
+ * followed by the 6 phases of the entropy kernel (pass 0, pass 1, chase, verify loop, scan, write): float[13] */
+int rmr_jpeg_decoder_profile(rmr_jpeg_decoder_t* dec, const void* file_bytes, size_t size, float* stage_ms13);
 /* test hook: quantised coefficient blocks of the last decode, int16 [n_blocks][64], scan order x natural order */
 int rmr_jpeg_decoder_read_coefficients(rmr_jpeg_decoder_t* dec, int16_t* out, long capacity_blocks, long* n_blocks);
 /* cv::imread + RobotDetector::detect without the raw frame ever crossing PCIe: decode on the decoder's stream,

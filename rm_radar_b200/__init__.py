@@ -464,15 +464,19 @@ class JpegDecoder:
         return frame.value, w.value, h.value
 
     def status(self) -> dict:
-        st, rounds, launches, up = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
-        _lib.check(self._lib.rmr_jpeg_decoder_status(self._h, C.byref(st), C.byref(rounds), C.byref(launches), C.byref(up)))
-        return dict(status=st.value, sync_rounds=rounds.value, kernel_launches=launches.value, upload_bytes=up.value)
+        st, rounds, dec, launches, up = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        _lib.check(self._lib.rmr_jpeg_decoder_status(self._h, C.byref(st), C.byref(rounds), C.byref(dec), C.byref(launches),
+                                                     C.byref(up)))
+        return dict(status=st.value, sync_rounds=rounds.value, loop_decodes=dec.value, kernel_launches=launches.value,
+                    upload_bytes=up.value)
 
     def profile(self, file_bytes: bytes) -> dict:
         """Device ms per stage of one decode (CUDA events between the launches)."""
-        ms = (C.c_float * 7)()
+        ms = (C.c_float * 13)()
         _lib.check(self._lib.rmr_jpeg_decoder_profile(self._h, file_bytes, len(file_bytes), ms))
-        return dict(zip(("upload", "clear", "unstuff", "entropy", "dc_scan", "idct", "colour"), (float(x) for x in ms)))
+        names = ("upload", "clear", "unstuff", "entropy", "dc_scan", "idct", "colour", "entropy.pass0", "entropy.pass1",
+                 "entropy.chase", "entropy.verify", "entropy.scan", "entropy.write")
+        return dict(zip(names, (float(x) for x in ms)))
 
     def coefficients(self, n_blocks: int) -> np.ndarray:
         """Quantised coefficient blocks of the last decode, int16 [n_blocks, 64] (scan order x natural order)."""

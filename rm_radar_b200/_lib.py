@@ -107,7 +107,7 @@ def load():
     lib.rmr_jpeg_info.argtypes = [vp, C.c_size_t] + [P(ci)] * 6
     lib.rmr_jpeg_decode.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, P(ci), P(ci)]
     lib.rmr_jpeg_decode_device.argtypes = [vp, vp, C.c_size_t, vp, ci, P(vp), P(ci), P(ci)]
-    lib.rmr_jpeg_decoder_status.argtypes = [vp, P(ci), P(ci), P(ci), P(C.c_size_t)]
+    lib.rmr_jpeg_decoder_status.argtypes = [vp, P(ci), P(ci), P(ci), P(ci), P(C.c_size_t)]
     lib.rmr_jpeg_decoder_profile.argtypes = [vp, vp, C.c_size_t, P(cf)]
     lib.rmr_jpeg_decoder_read_coefficients.argtypes = [vp, vp, C.c_long, P(C.c_long)]
     lib.rmr_robot_detector_detect_jpeg.argtypes = [vp, vp, vp, C.c_size_t, vp, ci, P(ci)]

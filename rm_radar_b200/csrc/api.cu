@@ -418,21 +418,22 @@ int rmr_jpeg_decode_device(rmr_jpeg_decoder_t* dec, const void* file_bytes, size
         if (frame) *frame = f;
     });
 }
-int rmr_jpeg_decoder_status(rmr_jpeg_decoder_t* dec, int* status, int* sync_rounds, int* kernel_launches,
-                            size_t* upload_bytes) {
+int rmr_jpeg_decoder_status(rmr_jpeg_decoder_t* dec, int* status, int* sync_rounds, int* loop_decodes,
+                            int* kernel_launches, size_t* upload_bytes) {
     return guarded([&] {
         if (!dec) throw std::invalid_argument("null argument");
         const int st = dec->impl->status();
         if (status) *status = st;
         if (sync_rounds) *sync_rounds = dec->impl->last_rounds();
+        if (loop_decodes) *loop_decodes = dec->impl->last_loop_decodes();
         if (kernel_launches) *kernel_launches = dec->impl->last_launches();
         if (upload_bytes) *upload_bytes = dec->impl->last_upload_bytes();
     });
 }
-int rmr_jpeg_decoder_profile(rmr_jpeg_decoder_t* dec, const void* file_bytes, size_t size, float* stage_ms7) {
+int rmr_jpeg_decoder_profile(rmr_jpeg_decoder_t* dec, const void* file_bytes, size_t size, float* stage_ms13) {
     return guarded([&] {
-        if (!dec || !file_bytes || !stage_ms7) throw std::invalid_argument("null argument");
-        dec->impl->profile(file_bytes, size, stage_ms7);
+        if (!dec || !file_bytes || !stage_ms13) throw std::invalid_argument("null argument");
+        dec->impl->profile(file_bytes, size, stage_ms13);
     });
 }
 int rmr_jpeg_decoder_read_coefficients(rmr_jpeg_decoder_t* dec, int16_t* out, long capacity_blocks, long* n_blocks) {

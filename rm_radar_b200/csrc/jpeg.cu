@@ -33,12 +33,23 @@ constexpr int kUnstuffThreads = 256, kUnstuffBytes = 16;            // bytes per
 constexpr int kDecodeThreads = 64;
 constexpr int kMaxRoundsSlack = 16;
 enum : int { CTRL_BARRIER = 0, CTRL_STATUS = 1, CTRL_ROUNDS = 2, CTRL_BYTES = 3, CTRL_MARKERS = 4, CTRL_BLOCKS = 5,
-             CTRL_CHANGED = 8 };
+             CTRL_DECODES = 6, CTRL_CHANGED = 8 };
 enum : int { ST_BLOCK_COUNT = 1, ST_INTERVALS = 2, ST_TAIL = 4 };
 
-constexpr int kLutBits = 11;
+constexpr int kLutBits = 10;
+// lookup entry: bits 0-5 bits consumed (code + magnitude), 6-12 zig-zag advance (64 = end of block), 13-17 code length,
+// 18-21 magnitude size s, 22-25 run r; 0 = the code is longer than kLutBits
+__host__ __device__ inline uint32_t lut_entry(int len, int sym, bool dc) {
+    const int s = sym & 15, r = dc ? 0 : sym >> 4;
+    const int zinc = dc ? 1 : (s ? r + 1 : (r == 15 ? 16 : 64));
+    return static_cast<uint32_t>(len + s) | (static_cast<uint32_t>(zinc) << 6) | (static_cast<uint32_t>(len) << 13) |
+           (static_cast<uint32_t>(s) << 18) | (static_cast<uint32_t>(r) << 22);
+}
+constexpr int kLut2 = 512;            // second level: the 16-bit prefixes at and above the first code longer than kLutBits
 struct JpegTables {
-    uint16_t lut[6][1 << kLutBits];   // [component * 2 + ac][next 11 bits] -> code length << 8 | symbol; 0: a longer code
+    uint32_t lut[6][1 << kLutBits];   // [component * 2 + ac][next 10 bits]
+    uint32_t lut2[6][kLut2];          // [table][16-bit prefix - base16[table]]
+    uint32_t base16[8];
     int maxcode[6][18];       // largest code of each length, -1 when the length is unused
     int valoff[6][18];        // index of the first symbol of the length minus its first code
     uint8_t vals[6][256];
@@ -61,6 +72,10 @@ struct JpegDev {
     uint32_t* intervals;
     int n_intervals;
     uint2* states;
+    uint2* cand;
+    uint4* res;
+    unsigned char* bmap;
+    unsigned long long* tstamp;   // phase boundaries of the entropy kernel (block 0), globaltimer ns
     int n_sub;
     uint32_t sub_bits;
     int* ctrl;
@@ -198,7 +213,9 @@ __global__ void __launch_bounds__(kUnstuffThreads) jpeg_unstuff_scatter_kernel(J
 // entropy decoding
 // ---------------------------------------------------------------------------------------------------------
 struct SmemTables {
-    uint16_t lut[6][1 << kLutBits];
+    uint32_t lut[6][1 << kLutBits];
+    uint32_t lut2[6][kLut2];
+    uint32_t base16[8];
     int maxcode[6][18];
     int valoff[6][18];
     uint8_t vals[6][256];
@@ -227,9 +244,20 @@ __device__ __forceinline__ void grid_barrier(int* counter, unsigned nblocks) {
 // Decodes from state `st` while the bit position is below `limit`; returns the end state.  state.x = bit position of
 // the next code, state.y = zig-zag index of the next coefficient | block-in-MCU << 8.  Defined for ANY start state
 // (speculative starts land inside codes): unknown codes consume 16 bits, run-aways end the block.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 template <bool kWrite>
 __device__ __forceinline__ uint2 decode_range(const JpegDev& J, const SmemTables& T, uint2 st, uint32_t limit, int& n_done,
-                                              long blk) {
+                                              long blk0) {
     const uint32_t* words = reinterpret_cast<const uint32_t*>(J.stream);
     uint32_t p = st.x;
     int z = st.y & 0xFF, c = st.y >> 8;
@@ -244,75 +272,91 @@ __device__ __forceinline__ uint2 decode_range(const JpegDev& J, const SmemTables
         k = lo;
     }
     uint32_t ivl_end = J.intervals[k + 1];
-    int comp = T.comp_of_block[c];
-    // 96-bit window over the big-endian stream: w0:w1 cover bits [32 wi, 32 wi + 64), w2 is the word after them,
-    // loaded one refill ahead so that its latency is off the per-symbol dependency chain
+    // component of block c of an MCU without a table lookup: blocks 0 .. bpm-3 are luma, then Cb, Cr
+    const int bpm = J.bpm, cshift = J.ncomp == 3 ? bpm - 3 : 1 << 20;
+    int comp = max(0, c - cshift);
+    uint32_t lut_base = smem_u32(&T.lut[0][0]);
+    asm volatile("" : "+r"(lut_base));   // keep the shared-window addresses in registers (no S2R in the loop)
+    constexpr uint32_t kAcOff = 4u << kLutBits;             // bytes per table: the AC table follows the DC table of a component
+    uint32_t toff = (static_cast<uint32_t>(comp) << (kLutBits + 3)) | (z ? kAcOff : 0u);
+    const bool multi = J.n_intervals > 1;
+    // write pass only: block and MCU counters of the block being filled
+    const int n_blocks = static_cast<int>(J.n_blocks);
+    int blk = static_cast<int>(blk0), mcu = kWrite ? static_cast<int>(blk0 / bpm) : 0;
+    int16_t* cptr = J.coef + (static_cast<size_t>(blk) << 6);
+    // 96-bit window over the big-endian stream: w0:w1 cover bits [32 wi, 32 wi + 64); r2 is the (not yet byte-swapped)
+    // word after them, loaded one refill ahead so that no load sits on the per-symbol dependency chain
     uint32_t wi = p >> 5;
     uint32_t w0 = __byte_perm(__ldg(words + wi), 0, 0x0123), w1 = __byte_perm(__ldg(words + wi + 1), 0, 0x0123),
-             w2 = __byte_perm(__ldg(words + wi + 2), 0, 0x0123);
+             r2 = __ldg(words + wi + 2);
+    uint32_t lut2_base = smem_u32(&T.lut2[0][0]);
+    asm volatile("" : "+r"(lut2_base));
     while (p < limit) {
         uint32_t off = p - (wi << 5);
-        if (off >= 32) {
-            if (off < 64) {
-                ++wi;
-                w0 = w1;
-                w1 = w2;
-                w2 = __byte_perm(__ldg(words + wi + 2), 0, 0x0123);
-            } else {                   // a jump over restart padding
-                wi = p >> 5;
-                w0 = __byte_perm(__ldg(words + wi), 0, 0x0123);
-                w1 = __byte_perm(__ldg(words + wi + 1), 0, 0x0123);
-                w2 = __byte_perm(__ldg(words + wi + 2), 0, 0x0123);
-            }
-            off = p - (wi << 5);
+        if (off >= 32) {               // at most one word per symbol (a symbol is <= 31 bits); jumps reload below
+            ++wi;
+            w0 = w1;
+            w1 = __byte_perm(r2, 0, 0x0123);
+            r2 = __ldg(words + wi + 2);
+            off -= 32;
         }
         const uint32_t w = __funnelshift_l(w1, w0, off);
-        const bool is_dc = z == 0;
-        const int t = comp * 2 + (is_dc ? 0 : 1);
-        const uint32_t e = T.lut[t][w >> (32 - kLutBits)];
-        int len = e >> 8, sym = e & 0xFF;
-        if (len == 0) {
-            len = 16;
-            sym = 0;
+        uint32_t e = lds_u32(lut_base + toff + ((w >> (30 - kLutBits)) & ((4u << kLutBits) - 4u)));
+        if (e == 0) {                                         // a code longer than kLutBits
+            const int t = static_cast<int>(toff >> (kLutBits + 2));
+            const uint32_t i2 = (w >> 16) - T.base16[t];
+            if (i2 < static_cast<uint32_t>(kLut2)) e = lds_u32(lut2_base + (static_cast<uint32_t>(t) * kLut2 + i2) * 4u);
+            if (e == 0) {                                     // beyond the second level (or no such code): canonical search
+                int len = 16, sym = 0;
 #pragma unroll 1
-            for (int l = kLutBits + 1; l <= 16; ++l) {
-                const int code = static_cast<int>(w >> (32 - l));
-                if (code <= T.maxcode[t][l]) {
-                    len = l;
-                    sym = T.vals[t][(code + T.valoff[t][l]) & 0xFF];
-                    break;
-                }
-            }
-        }
-        const int s = sym & 15, r = sym >> 4;
-        const uint32_t v = __funnelshift_l(w << len, 0u, s);            // the s bits after the code (0 when s = 0)
-        const int val = static_cast<int>(v) - (v < ((1u << s) >> 1) ? (1 << s) - 1 : 0);
-        p += len + s;
-        if (kWrite) {
-            const int idx = is_dc ? 0 : z + r;
-            if ((is_dc || s) && idx < 64 && blk < J.n_blocks) {
-                J.coef[blk * 64 + T.natural[idx]] = static_cast<int16_t>(val);   // DC: the difference; resolved by the DC scan
-                if (is_dc && val) atomicAdd(&J.mcu_dc[comp * J.n_mcus + static_cast<int>(blk / J.bpm)], val);
-            }
-        }
-        z = is_dc ? 1 : (s ? z + r + 1 : (r == 15 ? z + 16 : 64));
-        if (z >= 64) {
-            z = 0;
-            ++n_done;
-            ++blk;
-            c = c + 1 == J.bpm ? 0 : c + 1;
-            comp = T.comp_of_block[c];
-            if (c == 0 && (J.n_intervals > 1 || p + 8 > ivl_end)) {
-                // end of an MCU: fewer than 8 (padding) bits left in the interval -> continue at the next one
-                while (k + 1 < J.n_intervals && J.intervals[k + 1] <= p) ++k;
-                ivl_end = J.intervals[k + 1];
-                const uint32_t rem = ivl_end > p ? ivl_end - p : 0u;
-                if (rem < 8) {
-                    const bool pad = rem == 0 || J.bpm >= 3 || (peek32(words, p) >> (32 - rem)) == ((1u << rem) - 1u);
-                    if (pad) {
-                        p = max(p, ivl_end);
-                        if (k + 1 < J.n_intervals) { ++k; ivl_end = J.intervals[k + 1]; }
+                for (int l = kLutBits + 1; l <= 16; ++l) {
+                    const int code = static_cast<int>(w >> (32 - l));
+                    if (code <= T.maxcode[t][l]) {
+                        len = l;
+                        sym = T.vals[t][(code + T.valoff[t][l]) & 0xFF];
+                        break;
                     }
+                }
+                e = lut_entry(len, sym, z == 0);
+            }
+        }
+        p += e & 63u;
+        if (kWrite) {
+            const int s = (e >> 18) & 15, len = (e >> 13) & 31, idx = z + static_cast<int>((e >> 22) & 15u);
+            if ((z == 0 || s) && idx < 64 && blk < n_blocks) {
+                const uint32_t v = __funnelshift_l(w << len, 0u, s);            // the s bits after the code (0 when s = 0)
+                const int val = static_cast<int>(v) - (v < ((1u << s) >> 1) ? (1 << s) - 1 : 0);
+                cptr[idx] = static_cast<int16_t>(val);       // zig-zag position; DC: the difference, resolved by the DC scan
+                if (z == 0 && val) atomicAdd(&J.mcu_dc[comp * J.n_mcus + mcu], val);
+            }
+        }
+        z += static_cast<int>((e >> 6) & 127u);
+        const bool done = z >= 64;
+        z = done ? 0 : z;
+        n_done += done ? 1 : 0;
+        const int cn = c + 1 == bpm ? 0 : c + 1;
+        c = done ? cn : c;
+        comp = max(0, c - cshift);
+        toff = (static_cast<uint32_t>(comp) << (kLutBits + 3)) | (done ? 0u : kAcOff);
+        if (kWrite) {
+            blk += done ? 1 : 0;
+            cptr += done ? 64 : 0;
+            mcu += (done && c == 0) ? 1 : 0;
+        }
+        if (done && c == 0 && (multi || p + 8 > ivl_end)) {
+            // end of an MCU: fewer than 8 (padding) bits left in the interval -> continue at the next one
+            while (k + 1 < J.n_intervals && J.intervals[k + 1] <= p) ++k;
+            ivl_end = J.intervals[k + 1];
+            const uint32_t rem = ivl_end > p ? ivl_end - p : 0u;
+            if (rem < 8) {
+                const bool pad = rem == 0 || bpm >= 3 || (peek32(words, p) >> (32 - rem)) == ((1u << rem) - 1u);
+                if (pad) {
+                    p = max(p, ivl_end);
+                    if (k + 1 < J.n_intervals) { ++k; ivl_end = J.intervals[k + 1]; }
+                    wi = p >> 5;                               // the jump may skip words: reload the window
+                    w0 = __byte_perm(__ldg(words + wi), 0, 0x0123);
+                    w1 = __byte_perm(__ldg(words + wi + 1), 0, 0x0123);
+                    r2 = __ldg(words + wi + 2);
                 }
             }
         }
@@ -320,7 +364,7 @@ __device__ __forceinline__ uint2 decode_range(const JpegDev& J, const SmemTables
     return make_uint2(p, static_cast<uint32_t>(z) | (static_cast<uint32_t>(c) << 8));
 }
 
-__global__ void __launch_bounds__(kDecodeThreads) jpeg_entropy_kernel(JpegDev J) {
+__global__ void __launch_bounds__(kDecodeThreads) jpeg_entropy_simple_kernel(JpegDev J) {
     __shared__ SmemTables T;
     __shared__ int s_scan[kDecodeThreads];
     __shared__ int s_any;
@@ -328,7 +372,7 @@ __global__ void __launch_bounds__(kDecodeThreads) jpeg_entropy_kernel(JpegDev J)
         const uint32_t* src = reinterpret_cast<const uint32_t*>(J.tables);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
         // lut / maxcode / valoff / vals are the leading members of both structs, in the same order
-        constexpr int kWords = (sizeof(T.lut) + sizeof(T.maxcode) + sizeof(T.valoff) + sizeof(T.vals)) / 4;
+        constexpr int kWords = (sizeof(T.lut) + sizeof(T.lut2) + sizeof(T.base16) + sizeof(T.maxcode) + sizeof(T.valoff) + sizeof(T.vals)) / 4;
         for (int i = threadIdx.x; i < kWords; i += kDecodeThreads) dst[i] = src[i];
         if (threadIdx.x < 8) T.comp_of_block[threadIdx.x] = J.tables->comp_of_block[threadIdx.x];
         if (threadIdx.x < 64) T.natural[threadIdx.x] = kNatural[threadIdx.x];
@@ -407,6 +451,232 @@ __global__ void __launch_bounds__(kDecodeThreads) jpeg_entropy_kernel(JpegDev J)
             if (my_out.y != 0) atomicOr(&J.ctrl[CTRL_STATUS], ST_TAIL);
         }
     }
+}
+
+// The same fixed point reached in ~4 sequential passes instead of ~17.  A wrong guess survives because the block-in-MCU
+// index never self-synchronises, so every subsequence is decoded under all `bpm` hypotheses at once (8 lanes per
+// subsequence, lane = block-in-MCU guess):
+//   pass 0   lane k of subsequence i decodes from (first bit of i, DC expected, block k)  -> candidate states of boundary i+1
+//   pass 1   lane k decodes subsequence i from candidate k of boundary i (a real state, whoever produced it) -> result,
+//            and the index of that result among the candidates of boundary i+1 (the link; the true chain finds its
+//            successor there for ~99 % of the boundaries)
+//   chase    links are followed from (boundary 0, lane 0) in shared memory: per block over its 32 subsequences for every
+//            entry lane, then over the per-block maps, then again inside the block from its true entry lane.  A dead
+//            link is continued at lane 0 of the next boundary (a placeholder the verify loop replaces).
+//   verify   the fixed-point loop of the simple kernel, seeded with the chased (input, output, count) triples.  A thread
+//            whose input changes first looks the new input up among its candidates (pass-1 results are real decodes of
+//            this subsequence) and only decodes when it is not there.  Every triple a thread holds is a genuine
+//            f_i(input), so the loop still ends exactly at the sequential decode.
+constexpr int kLanes = 8, kSubsPerBlock = 32, kHypThreads = kLanes * kSubsPerBlock, kMaxHypBlocks = 592;
+constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+__device__ __forceinline__ void stamp(const JpegDev& J, int slot) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        J.tstamp[slot] = t;
+    }
+}
+constexpr unsigned kDead = 0x80u;
+
+__global__ void __launch_bounds__(kHypThreads) jpeg_entropy_kernel(JpegDev J) {
+    __shared__ SmemTables T;
+    __shared__ int s_scan[kHypThreads];
+    __shared__ int s_any;
+    __shared__ unsigned char s_link[kSubsPerBlock][kLanes];
+    __shared__ unsigned char s_sel[kSubsPerBlock];
+    __shared__ unsigned char s_bmap[kMaxHypBlocks][kLanes];
+    __shared__ long s_before[kHypThreads / 32];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(J.tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
+        constexpr int kWords = (sizeof(T.lut) + sizeof(T.lut2) + sizeof(T.base16) + sizeof(T.maxcode) + sizeof(T.valoff) + sizeof(T.vals)) / 4;
+        for (int i = threadIdx.x; i < kWords; i += kHypThreads) dst[i] = src[i];
+        if (threadIdx.x < 8) T.comp_of_block[threadIdx.x] = J.tables->comp_of_block[threadIdx.x];
+        if (threadIdx.x < 64) T.natural[threadIdx.x] = kNatural[threadIdx.x];
+    }
+    __syncthreads();
+    const int sub = threadIdx.x >> 3, lane = threadIdx.x & 7;
+    const int i = blockIdx.x * kSubsPerBlock + sub;
+    const uint32_t total_bits = static_cast<uint32_t>(J.ctrl[CTRL_BYTES]) * 8u;
+    const int n_sub = static_cast<int>((static_cast<unsigned long long>(total_bits) + J.sub_bits - 1) / J.sub_bits);
+    const bool active = i < n_sub, owner = active && lane == 0, hyp = active && lane < J.bpm;
+    const uint32_t lo = static_cast<uint32_t>(i) * J.sub_bits;
+    const uint32_t hi = active ? static_cast<uint32_t>(min(static_cast<unsigned long long>(lo) + J.sub_bits,
+                                                           static_cast<unsigned long long>(total_bits))) : 0u;
+    uint2* cand = J.cand;            // [n_sub + 1][kLanes]
+    uint4* res = J.res;              // [n_sub][kLanes]: end state, blocks completed, link
+
+    stamp(J, 0);
+    // ---- pass 0: candidates of every boundary ----
+    if (active) {
+        uint2 e = make_uint2(kInvalid, kInvalid);
+        if (hyp) {
+            int n = 0;
+            e = decode_range<false>(J, T, make_uint2(lo, static_cast<uint32_t>(lane) << 8), hi, n, 0);
+        }
+        __stcg(cand + static_cast<size_t>(i + 1) * kLanes + lane, e);
+        if (i == 0) __stcg(cand + lane, lane == 0 ? make_uint2(0u, 0u) : make_uint2(kInvalid, kInvalid));
+    }
+    grid_barrier(&J.ctrl[CTRL_BARRIER], gridDim.x);
+    stamp(J, 1);
+
+    // ---- pass 1: decode from every candidate, link the result to the candidates of the next boundary ----
+    unsigned link = kDead;
+    if (hyp) {
+        const uint2 in = __ldcg(cand + static_cast<size_t>(i) * kLanes + lane);
+        uint2 x = make_uint2(kInvalid, kInvalid);
+        int n = 0;
+        if (in.x != kInvalid) {
+            x = decode_range<false>(J, T, in, hi, n, 0);
+            if (i + 1 < n_sub) {
+                for (int k = 0; k < J.bpm; ++k) {
+                    const uint2 c = __ldcg(cand + static_cast<size_t>(i + 1) * kLanes + k);
+                    if (c.x == x.x && c.y == x.y) { link = static_cast<unsigned>(k); break; }
+                }
+            } else {
+                link = 0;
+            }
+        }
+        __stcg(res + static_cast<size_t>(i) * kLanes + lane, make_uint4(x.x, x.y, static_cast<uint32_t>(n), link));
+    }
+    s_link[sub][lane] = static_cast<unsigned char>(link);
+    __syncthreads();
+
+    // ---- chase, level 1: exit lane of this block for every entry lane ----
+    if (threadIdx.x < kLanes) {
+        unsigned k = threadIdx.x, dead = 0;
+        for (int s2 = 0; s2 < kSubsPerBlock; ++s2) {
+            if (static_cast<int>(blockIdx.x) * kSubsPerBlock + s2 >= n_sub) break;
+            const unsigned l = s_link[s2][k];
+            dead = l & kDead;
+            k = dead ? 0u : l;
+        }
+        J.bmap[static_cast<size_t>(blockIdx.x) * kLanes + threadIdx.x] = static_cast<unsigned char>(k | dead);
+    }
+    grid_barrier(&J.ctrl[CTRL_BARRIER], gridDim.x);
+    stamp(J, 2);
+    // ---- level 2: entry lane of this block = the maps of all blocks before it applied to lane 0 ----
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(J.bmap);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_bmap[0][0]);
+        for (int w = threadIdx.x; w < static_cast<int>(blockIdx.x) * (kLanes / 4); w += kHypThreads) dst[w] = __ldcg(src + w);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned k = 0, dead = 0;
+        for (int b = 0; b < static_cast<int>(blockIdx.x); ++b) {
+            const unsigned m = s_bmap[b][k];
+            dead = m & kDead;
+            k = m & 7u;
+        }
+        // ---- level 3: true lane of every subsequence of this block ----
+        (void)dead;
+        for (int s2 = 0; s2 < kSubsPerBlock; ++s2) {
+            s_sel[s2] = static_cast<unsigned char>(k);      // after a dead link: lane 0 as a placeholder (a genuine triple)
+            const unsigned l = s_link[s2][k];
+            k = (l & kDead) ? 0u : l;
+        }
+    }
+    __syncthreads();
+
+    // ---- seed the fixed-point loop with the chased triples ----
+    uint2 my_in = make_uint2(kInvalid, kInvalid), my_out = make_uint2(kInvalid, kInvalid);
+    int my_n = 0;
+    const int stride = J.n_sub + 1;
+    if (owner) {
+        const unsigned sel = s_sel[sub] & 7u;
+        const uint2 c = __ldcg(cand + static_cast<size_t>(i) * kLanes + sel);
+        const uint4 r = __ldcg(res + static_cast<size_t>(i) * kLanes + sel);
+        if (c.x != kInvalid) {
+            my_in = c;
+            my_out = make_uint2(r.x, r.y);
+            my_n = static_cast<int>(r.z);
+        }
+        __stcg(J.states + stride + i + 1, my_out);       // read as `cur` by round 1
+    }
+    grid_barrier(&J.ctrl[CTRL_BARRIER], gridDim.x);
+    stamp(J, 3);
+    int round = 1, decodes = 0;
+    for (;;) {
+        const uint2* cur = J.states + (round & 1) * stride;
+        uint2* nxt = J.states + ((round + 1) & 1) * stride;
+        bool redo = false;
+        if (owner) {
+            const uint2 in = i == 0 ? make_uint2(0u, 0u) : __ldcg(cur + i);
+            if (in.x != my_in.x || in.y != my_in.y) {
+                my_in = in;
+                redo = true;
+                bool found = false;
+                if (in.x != kInvalid) {
+                    for (int k = 0; k < J.bpm && !found; ++k) {
+                        const uint2 c = __ldcg(cand + static_cast<size_t>(i) * kLanes + k);
+                        if (c.x == in.x && c.y == in.y) {
+                            const uint4 r = __ldcg(res + static_cast<size_t>(i) * kLanes + k);
+                            my_out = make_uint2(r.x, r.y);
+                            my_n = static_cast<int>(r.z);
+                            found = true;
+                        }
+                    }
+                }
+                if (!found) {
+                    my_n = 0;
+                    my_out = decode_range<false>(J, T, in, hi, my_n, 0);
+                    ++decodes;
+                }
+            }
+            __stcg(nxt + i + 1, my_out);
+        }
+        if (threadIdx.x == 0) s_any = 0;
+        __syncthreads();
+        if (redo) s_any = 1;
+        __syncthreads();
+        if (threadIdx.x == 0 && s_any) atomicAdd(&J.ctrl[CTRL_CHANGED + round], 1);
+        grid_barrier(&J.ctrl[CTRL_BARRIER], gridDim.x);
+        const int changed = *reinterpret_cast<volatile int*>(&J.ctrl[CTRL_CHANGED + round]);
+        ++round;
+        if (changed == 0 || round >= n_sub + kMaxRoundsSlack - 1) break;
+    }
+    if (decodes) atomicMax(&J.ctrl[CTRL_DECODES], decodes);
+    stamp(J, 4);
+    // ---- output position of every subsequence: exclusive scan of the blocks each one completes ----
+    s_scan[threadIdx.x] = owner ? my_n : 0;
+    __syncthreads();
+    for (int o = 1; o < kHypThreads; o <<= 1) {
+        int t = 0;
+        if (threadIdx.x >= o) t = s_scan[threadIdx.x - o];
+        __syncthreads();
+        s_scan[threadIdx.x] += t;
+        __syncthreads();
+    }
+    if (threadIdx.x == kHypThreads - 1) __stcg(&J.grid_sums[blockIdx.x], s_scan[threadIdx.x]);
+    grid_barrier(&J.ctrl[CTRL_BARRIER], gridDim.x);
+    long before = 0;
+    for (int b = threadIdx.x; b < static_cast<int>(blockIdx.x); b += kHypThreads) before += __ldcg(&J.grid_sums[b]);
+    stamp(J, 5);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if ((threadIdx.x & 31) == 0) s_before[threadIdx.x >> 5] = before;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long t = 0;
+        for (int j = 0; j < kHypThreads / 32; ++j) t += s_before[j];
+        s_before[0] = t;
+    }
+    __syncthreads();
+    if (owner) {
+        const long blk0 = s_before[0] + s_scan[threadIdx.x] - my_n;
+        int n2 = 0;
+        decode_range<true>(J, T, my_in, hi, n2, blk0);
+        if (i == n_sub - 1) {
+            const long total = blk0 + my_n;
+            J.ctrl[CTRL_BLOCKS] = static_cast<int>(total);
+            J.ctrl[CTRL_ROUNDS] = round;
+            if (total != J.n_blocks) atomicOr(&J.ctrl[CTRL_STATUS], ST_BLOCK_COUNT);
+            if (my_out.y != 0) atomicOr(&J.ctrl[CTRL_STATUS], ST_TAIL);
+        }
+    }
+    __syncthreads();
+    stamp(J, 6);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -504,6 +774,10 @@ __global__ void __launch_bounds__(128) jpeg_idct_kernel(JpegDev J) {
     const int j = kb - first;
     const int hs = comp == 0 ? J.hs : 1, vs = comp == 0 ? J.vs : 1;
     const int x = ((mcu % J.mcus_x) * hs + j % hs) * 8, y = ((mcu / J.mcus_x) * vs + j / hs) * 8;
+    // the entropy stage stores coefficients at their zig-zag position; the natural order is applied here, at compile time
+    constexpr int kNat[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                              41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                              30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
     int v[64];
     const uint4* src = reinterpret_cast<const uint4*>(J.coef + blk * 64);
 #pragma unroll
@@ -513,7 +787,7 @@ __global__ void __launch_bounds__(128) jpeg_idct_kernel(JpegDev J) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const int raw = static_cast<int16_t>((w[c >> 1] >> (16 * (c & 1))) & 0xFFFF);
-            v[r * 8 + c] = raw;
+            v[kNat[r * 8 + c]] = raw;
         }
     }
     int dc = J.mcu_dc[comp * J.n_mcus + mcu] + v[0];
@@ -614,20 +888,34 @@ const uint8_t kNaturalHost[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25
                                   41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                   30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
-// canonical code tables of one DHT entry -> the 11-bit lookup table and the per-length limits
-void build_table(const uint8_t* bits, const uint8_t* vals, uint16_t* lut, int* maxcode, int* valoff, uint8_t* vals_out) {
-    std::memset(lut, 0, (1 << kLutBits) * sizeof(uint16_t));
+// canonical code tables of one DHT entry -> the kLutBits lookup table and the per-length limits
+void build_table(const uint8_t* bits, const uint8_t* vals, bool dc, uint32_t* lut, uint32_t* lut2, uint32_t* base16, int* maxcode,
+                 int* valoff, uint8_t* vals_out) {
+    std::memset(lut, 0, (1 << kLutBits) * sizeof(uint32_t));
     int code = 0, k = 0;
     for (int l = 1; l <= 16; ++l) {
         valoff[l] = k - code;
         for (int i = 0; i < bits[l]; ++i, ++k, ++code) {
             if (l <= kLutBits) {
                 const int first = code << (kLutBits - l);
-                for (int f = 0; f < (1 << (kLutBits - l)); ++f) lut[first + f] = static_cast<uint16_t>((l << 8) | vals[k]);
+                for (int f = 0; f < (1 << (kLutBits - l)); ++f) lut[first + f] = lut_entry(l, vals[k], dc);
             }
         }
         maxcode[l] = bits[l] ? code - 1 : -1;
         if (code > (1 << l)) bad("over-subscribed Huffman table");
+        if (l == kLutBits) *base16 = static_cast<uint32_t>(code) << (16 - kLutBits);   // first 16-bit prefix of a longer code
+        code <<= 1;
+    }
+    // second level: every 16-bit prefix from base16 on that starts a code of kLutBits+1 .. 16 bits
+    std::memset(lut2, 0, kLut2 * sizeof(uint32_t));
+    code = 0;
+    k = 0;
+    for (int l = 1; l <= 16; ++l) {
+        for (int i = 0; i < bits[l]; ++i, ++k, ++code) {
+            if (l <= kLutBits) continue;
+            const uint32_t first = (static_cast<uint32_t>(code) << (16 - l)) - *base16;
+            for (uint32_t f = 0; f < (1u << (16 - l)) && first + f < static_cast<uint32_t>(kLut2); ++f) lut2[first + f] = lut_entry(l, vals[k], dc);
+        }
         code <<= 1;
     }
     maxcode[0] = -1;
@@ -777,11 +1065,21 @@ JpegDecoder::JpegDecoder(int device) : device_(device) {
     RMR_CUDA(cudaGetDeviceProperties(&prop, device_));
     if (prop.major != 10) throw std::runtime_error("rm_radar_b200: sm_100 (B200) required, found sm_" + std::to_string(prop.major * 10 + prop.minor));
     int per_sm = 0;
-    RMR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jpeg_entropy_kernel, kDecodeThreads, 0));
+    RMR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jpeg_entropy_simple_kernel, kDecodeThreads, 0));
     max_coresident_ = per_sm * prop.multiProcessorCount;
     RMR_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     RMR_CUDA(cudaEventCreateWithFlags(&staged_, cudaEventDisableTiming));
     RMR_CUDA(cudaMalloc(&tables_, sizeof(JpegTables)));
+    RMR_CUDA(cudaMalloc(&bmap_, kMaxHypBlocks * kLanes));
+    RMR_CUDA(cudaMalloc(&tstamp_, 8 * sizeof(unsigned long long)));
+    RMR_CUDA(cudaMemset(tstamp_, 0, 8 * sizeof(unsigned long long)));
+    {
+        const char* e = std::getenv("RMR_JPEG_SIMPLE");
+        simple_ = e && e[0] == '1';
+        int hyp_per_sm = 0;
+        RMR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hyp_per_sm, jpeg_entropy_kernel, kHypThreads, 0));
+        max_hyp_blocks_ = std::min(hyp_per_sm * prop.multiProcessorCount, kMaxHypBlocks);
+    }
     RMR_CUDA(cudaMallocHost(&pinned_status_, 8 * sizeof(int)));
     std::memset(pinned_status_, 0, 8 * sizeof(int));
 }
@@ -796,6 +1094,10 @@ JpegDecoder::~JpegDecoder() {
     cudaFree(blk_offsets_);
     cudaFree(intervals_);
     cudaFree(states_);
+    cudaFree(cand_);
+    cudaFree(res_);
+    cudaFree(bmap_);
+    cudaFree(tstamp_);
     cudaFree(changed_);
     cudaFree(coef_);
     cudaFree(dc_abs_);
@@ -833,6 +1135,8 @@ void JpegDecoder::reserve(const JpegHeader& h) {
         regrow(blk_offsets_, ub);
         cap_sub_ = static_cast<long>(cap_raw_ * 8 / 256 + 2);      // never cut finer than 256 bits
         regrow(states_, 2 * static_cast<size_t>(cap_sub_ + 1));
+        regrow(cand_, static_cast<size_t>(cap_sub_ + 1) * kLanes);
+        regrow(res_, static_cast<size_t>(cap_sub_) * kLanes);
         regrow(changed_, static_cast<size_t>(CTRL_CHANGED + cap_sub_ + kMaxRoundsSlack + max_coresident_ + 64));
     }
     if (h.n_blocks > cap_blocks_) {
@@ -881,9 +1185,10 @@ const uint8_t* JpegDecoder::decode(const void* file, size_t size, uint8_t* dev_b
     std::memset(T, 0, sizeof(JpegTables));
     int kb = 0;
     for (int c = 0; c < h.components; ++c) {
-        build_table(h.bits[0][h.dc_of[c]], h.vals[0][h.dc_of[c]], T->lut[2 * c], T->maxcode[2 * c], T->valoff[2 * c], T->vals[2 * c]);
-        build_table(h.bits[1][h.ac_of[c]], h.vals[1][h.ac_of[c]], T->lut[2 * c + 1], T->maxcode[2 * c + 1], T->valoff[2 * c + 1],
-                    T->vals[2 * c + 1]);
+        build_table(h.bits[0][h.dc_of[c]], h.vals[0][h.dc_of[c]], true, T->lut[2 * c], T->lut2[2 * c], &T->base16[2 * c], T->maxcode[2 * c],
+                    T->valoff[2 * c], T->vals[2 * c]);
+        build_table(h.bits[1][h.ac_of[c]], h.vals[1][h.ac_of[c]], false, T->lut[2 * c + 1], T->lut2[2 * c + 1], &T->base16[2 * c + 1],
+                    T->maxcode[2 * c + 1], T->valoff[2 * c + 1], T->vals[2 * c + 1]);
         std::memcpy(T->quant[c], h.quant[h.quant_of[c]], sizeof(T->quant[c]));
         T->first_block_of_comp[c] = static_cast<uint8_t>(kb);
         const int nb = c == 0 ? h.h_samp * h.v_samp : 1;
@@ -911,11 +1216,17 @@ const uint8_t* JpegDecoder::decode(const void* file, size_t size, uint8_t* dev_b
     static const int env_bits = [] { const char* e = std::getenv("RMR_JPEG_SUB_BITS"); return e ? std::atoi(e) : 0; }();
     uint32_t sub_bits = env_bits >= 256 ? static_cast<uint32_t>(env_bits) / 32 * 32 : 1024;
     const unsigned long long raw_bits = static_cast<unsigned long long>(h.scan_bytes) * 8;
-    const unsigned long long max_threads = static_cast<unsigned long long>(max_coresident_) * kDecodeThreads;
-    if ((raw_bits + sub_bits - 1) / sub_bits > max_threads)
-        sub_bits = static_cast<uint32_t>(round_up((raw_bits + max_threads - 1) / max_threads, 32));
+    // every subsequence needs a resident thread (simple kernel) or 8 resident lanes (hypothesis kernel)
+    const unsigned long long max_subs = simple_ ? static_cast<unsigned long long>(max_coresident_) * kDecodeThreads
+                                                : static_cast<unsigned long long>(max_hyp_blocks_) * kSubsPerBlock;
+    if ((raw_bits + sub_bits - 1) / sub_bits > max_subs)
+        sub_bits = static_cast<uint32_t>(round_up((raw_bits + max_subs - 1) / max_subs, 32));
     J.sub_bits = sub_bits;
     J.n_sub = static_cast<int>((raw_bits + sub_bits - 1) / sub_bits);
+    J.cand = cand_;
+    J.res = res_;
+    J.bmap = bmap_;
+    J.tstamp = tstamp_;
     J.ctrl = changed_;
     J.grid_sums = changed_ + CTRL_CHANGED + cap_sub_ + kMaxRoundsSlack;
     J.coef = coef_;
@@ -954,10 +1265,16 @@ const uint8_t* JpegDecoder::decode(const void* file, size_t size, uint8_t* dev_b
     jpeg_unstuff_scatter_kernel<<<J.n_ublocks, kUnstuffThreads, 0, stream_>>>(J);
     mark();
     {
-        const int grid = (J.n_sub + kDecodeThreads - 1) / kDecodeThreads;
         void* args[] = {&J};
-        RMR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(jpeg_entropy_kernel), dim3(grid), dim3(kDecodeThreads),
-                                             args, 0, stream_));
+        if (simple_) {
+            const int grid = (J.n_sub + kDecodeThreads - 1) / kDecodeThreads;
+            RMR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(jpeg_entropy_simple_kernel), dim3(grid),
+                                                 dim3(kDecodeThreads), args, 0, stream_));
+        } else {
+            const int grid = (J.n_sub + kSubsPerBlock - 1) / kSubsPerBlock;
+            RMR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(jpeg_entropy_kernel), dim3(grid), dim3(kHypThreads),
+                                                 args, 0, stream_));
+        }
     }
     mark();
     jpeg_dc_scan_kernel<<<h.components, 1024, 0, stream_>>>(J);
@@ -987,11 +1304,20 @@ void JpegDecoder::profile(const void* file, size_t size, float* stage_ms) {
     profiling_ = false;
     RMR_CUDA(cudaStreamSynchronize(stream_));
     for (int i = 0; i < kStages; ++i) RMR_CUDA(cudaEventElapsedTime(&stage_ms[i], stage_ev_[i], stage_ev_[i + 1]));
+    // phases of the entropy kernel as block 0 saw them: pass 0, pass 1 + chase level 1, chase + seed, verify loop, scan, write
+    unsigned long long t[8] = {};
+    RMR_CUDA(cudaMemcpy(t, tstamp_, sizeof(t), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 6; ++i) stage_ms[kStages + i] = simple_ ? 0.f : static_cast<float>(static_cast<double>(t[i + 1] - t[i]) * 1e-6);
 }
 
 int JpegDecoder::status() {
     RMR_CUDA(cudaStreamSynchronize(stream_));
     return pinned_status_[CTRL_STATUS];
+}
+
+int JpegDecoder::last_loop_decodes() {
+    RMR_CUDA(cudaStreamSynchronize(stream_));
+    return pinned_status_[CTRL_DECODES];
 }
 
 int JpegDecoder::last_rounds() {
@@ -1015,10 +1341,13 @@ long JpegDecoder::read_coefficients(int16_t* out, long capacity_blocks) {
     const long n = last_.n_blocks;
     if (out == nullptr || capacity_blocks < n) throw std::invalid_argument("jpeg: coefficient buffer too small");
     RMR_CUDA(cudaStreamSynchronize(stream_));
-    RMR_CUDA(cudaMemcpy(out, coef_, static_cast<size_t>(n) * 64 * sizeof(int16_t), cudaMemcpyDeviceToHost));
-    std::vector<int16_t> dc(static_cast<size_t>(n));
-    RMR_CUDA(cudaMemcpy(dc.data(), dc_abs_, static_cast<size_t>(n) * sizeof(int16_t), cudaMemcpyDeviceToHost));
-    for (long b = 0; b < n; ++b) out[b * 64] = dc[static_cast<size_t>(b)];
+    std::vector<int16_t> zz(static_cast<size_t>(n) * 64), dc(static_cast<size_t>(n));
+    RMR_CUDA(cudaMemcpy(zz.data(), coef_, zz.size() * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    RMR_CUDA(cudaMemcpy(dc.data(), dc_abs_, dc.size() * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    for (long b = 0; b < n; ++b) {        // device layout: zig-zag order, DC as a difference
+        for (int k = 0; k < 64; ++k) out[b * 64 + kNaturalHost[k]] = zz[static_cast<size_t>(b) * 64 + k];
+        out[b * 64] = dc[static_cast<size_t>(b)];
+    }
     return n;
 }
 

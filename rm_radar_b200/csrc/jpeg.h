@@ -50,8 +50,10 @@ public:
     long read_coefficients(int16_t* out, long capacity_blocks);
     int last_launches() const { return last_launches_; }
     int last_rounds();                  // synchronisation rounds the entropy decoder needed (after status())
+    int last_loop_decodes();            // most re-decodes any one thread did in the verification loop
     size_t last_upload_bytes() const { return last_upload_; }
-    // stage timing of one decode (CUDA events between the launches): upload, clear, unstuff, entropy, dc scan, idct, colour
+    // stage timing of one decode (CUDA events between the launches): upload, clear, unstuff, entropy, dc scan, idct, colour;
+    // stage_ms holds kStages + 6 floats: the last six split the entropy kernel (globaltimer stamps of block 0)
     static constexpr int kStages = 7;
     void profile(const void* file, size_t size, float* stage_ms);
 
@@ -69,6 +71,12 @@ private:
     int2 *blk_counts_ = nullptr, *blk_offsets_ = nullptr;
     uint32_t* intervals_ = nullptr;     // start bit of every restart interval + the end of the stream
     uint2* states_ = nullptr;           // [2][n_sub + 1]
+    uint2* cand_ = nullptr;             // [n_sub + 1][8] candidate states per subsequence boundary
+    uint4* res_ = nullptr;              // [n_sub][8] decode results from each candidate
+    unsigned char* bmap_ = nullptr;     // per-block lane maps of the link chase
+    unsigned long long* tstamp_ = nullptr;
+    bool simple_ = false;               // RMR_JPEG_SIMPLE=1: single-hypothesis kernel
+    int max_hyp_blocks_ = 0;
     int* sub_blocks_ = nullptr;         // blocks completed per subsequence
     int* changed_ = nullptr;            // per-round change counters + grid barrier + status words
     int16_t *coef_ = nullptr, *dc_abs_ = nullptr;
