@@ -1,7 +1,7 @@
 /* dev analysis: how far does a speculative decode (guess: block of component c starts at bit i*S) run before it merges
- * with the true parse?  gcc -O2 -o jpeg_sync_sim jpeg_sync_sim.c && ./jpeg_sync_sim file.jpg [S] */
+ * with the true parse?  gcc -O2 -o tools/jpeg_sync_sim tools/jpeg_sync_sim.c && ./jpeg_sync_sim file.jpg [S] */
 #include <stdio.h>
-#include "../../oracle/jpeg_ref.c"
+#include "../oracle/jpeg_ref.c"
 
 static uint8_t* U; static size_t NU;   /* unstuffed stream */
 static uint32_t peekU(size_t p) { uint64_t v = 0; size_t b = p >> 3; for (int k = 0; k < 8; ++k) v = (v << 8) | (b + k < NU ? U[b + k] : 0xFF); return (uint32_t)((v << (p & 7)) >> 32); }
