@@ -143,7 +143,13 @@ def run_smoke(verbose=False):
     for c in (clouds["background"], clouds["c0"]):
         loc.update(c); ora.update(c)
     loc.cluster(); ora.cluster()
-    robots = det.detect(img)
+    # the frame enters as the JPEG file the reference would cv::imread: decoded on the device, checked against the oracle
+    from oracle import jpeg_oracle as jo
+    jpg = open(os.path.join(GOLDEN, "frames", "0.jpg"), "rb").read()
+    dec = rr.JpegDecoder(0)
+    assert np.array_equal(dec.decode(jpg), jo.decode(jpg)), "device JPEG decode differs from the oracle"
+    assert np.array_equal(img, jo.decode(jpg)), "oracle JPEG decode differs from cv2.imread"
+    robots = det.detect_jpeg(dec, jpg)
     loc.search(robots)
     cars = [d.as_array() for d in det.last_cars()]
     match_detections(cars, exp["f0_cars"])
