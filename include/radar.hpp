@@ -19,6 +19,8 @@
 #include <array>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <chrono>
 #include <optional>
 #include <ostream>
 #include <stdexcept>
@@ -118,6 +120,8 @@ inline int lround_half_even(float v) noexcept {   // cvRound
 }  // namespace detail
 
 // radar::Robot — src/robot/robot.h:53-164 (tracking members are out of scope of the hot path)
+enum class TrackState { Tentative, Confirmed, Deleted };   // src/track/track.h:25
+
 class Robot {
    public:
     Robot() = default;
@@ -134,6 +138,10 @@ class Robot {
     inline std::optional<float> confidence() const noexcept { return confidence_; }
     inline std::optional<std::vector<Detection>> armors() const noexcept { return armors_; }
     inline std::optional<Point3f> location() const noexcept { return location_; }
+    // robot.h:81,139-141: set by Tracker::update (Robot::setTrack, robot.cpp:81-94)
+    inline bool isTracked() const noexcept { return track_state_.has_value(); }
+    inline std::optional<TrackState> track_state() const noexcept { return track_state_; }
+    inline std::optional<int> track_id() const noexcept { return track_id_; }
     // metres, world frame: the C ABI already applied setLocation's mm -> m (robot.h:93-95)
     inline void setLocationMetres(const Point3f& p) noexcept { location_ = p; }
 
@@ -177,6 +185,31 @@ class Robot {
         rec.label = label_.value_or(-1);
         rec.cluster = -2;
     }
+    // every field the tracker reads (Robot::feature, robot.cpp:102-122, needs the armours)
+    void toFullRecord(rmr_robot_t& rec) const noexcept {
+        toRecord(rec);
+        if (armors_) {
+            rec.is_detected = 1;
+            rec.confidence = confidence_.value_or(0.f);
+            rec.n_armors = static_cast<int32_t>(std::min<size_t>(armors_->size(), RMR_MAX_ARMORS));
+            for (int i = 0; i < rec.n_armors; ++i) {
+                const Detection& d = (*armors_)[static_cast<size_t>(i)];
+                rec.armors[i] = rmr_detection_t{d.x, d.y, d.width, d.height, d.label, d.confidence};
+            }
+        }
+        if (location_) {
+            rec.is_located = 1;
+            rec.location[0] = location_->x; rec.location[1] = location_->y; rec.location[2] = location_->z;
+        }
+    }
+    // Robot::setTrack as the C ABI reports it: state / id of the matched track, label and location after the update
+    void applyTrack(const rmr_robot_t& rec, int state, int id) noexcept {
+        if (state < 0) return;
+        track_state_ = static_cast<TrackState>(state);
+        track_id_ = id;
+        if (rec.label >= 0) label_ = rec.label;
+        if (rec.is_located) location_ = Point3f{rec.location[0], rec.location[1], rec.location[2]};
+    }
 
    private:
     std::optional<std::vector<Detection>> armors_ = std::nullopt;
@@ -184,6 +217,8 @@ class Robot {
     std::optional<Rect2f> rect_ = std::nullopt;
     std::optional<int> label_ = std::nullopt;
     std::optional<float> confidence_ = std::nullopt;
+    std::optional<TrackState> track_state_ = std::nullopt;
+    std::optional<int> track_id_ = std::nullopt;
 };
 
 // radar::Detector — src/detect/detector.h:84-134
@@ -441,6 +476,52 @@ class Locator {
 
 // One frame of the whole path — the body of SampleRadar::runOnce (samples/sample_radar.h:106-127) without the
 // tracker and the GUI: Locator::update + cluster overlap with RobotDetector::detect, then Locator::search.
+// radar::Tracker -- src/track/tracker.h:23-53.  Same constructor arguments and defaults; update() takes the robots of
+// one frame and their time stamp, and marks / completes them the way Robot::setTrack does.
+class Tracker {
+   public:
+    Tracker(const Tracker&) = delete;
+    Tracker& operator=(const Tracker&) = delete;
+    Tracker(const Point3f& observation_noise, int class_num, int init_thresh = 4, int miss_thresh = 10,
+            float max_acceleration = 2.0f, float acceleration_correlation_time = 1.0f, float distance_weight = 0.40f,
+            float feature_weight = 0.60f, int max_iter = 100, float distance_thresh = 0.8f) {
+        const float noise[3] = {observation_noise.x, observation_noise.y, observation_noise.z};
+        detail::throw_status(rmr_tracker_create(&handle_, noise, class_num, init_thresh, miss_thresh, max_acceleration,
+                                                acceleration_correlation_time, distance_weight, feature_weight, max_iter,
+                                                distance_thresh));
+    }
+    ~Tracker() { rmr_tracker_destroy(handle_); }
+
+    void update(std::vector<Robot>& robots, const std::chrono::high_resolution_clock::time_point& timestamp) {
+        update(robots, std::chrono::duration_cast<std::chrono::nanoseconds>(timestamp.time_since_epoch()).count());
+    }
+    void update(std::vector<Robot>& robots, long long timestamp_ns) {
+        const int n = static_cast<int>(robots.size());
+        records_.resize(robots.size());
+        state_.assign(robots.size(), -1);
+        id_.assign(robots.size(), -1);
+        for (int i = 0; i < n; ++i) robots[static_cast<size_t>(i)].toFullRecord(records_[static_cast<size_t>(i)]);
+        if (rmr_tracker_update(handle_, records_.data(), n, timestamp_ns, state_.data(), id_.data()) != RMR_OK)
+            detail::fatal("Tracker::update");
+        for (int i = 0; i < n; ++i)
+            robots[static_cast<size_t>(i)].applyTrack(records_[static_cast<size_t>(i)], state_[static_cast<size_t>(i)],
+                                                      id_[static_cast<size_t>(i)]);
+    }
+    std::vector<rmr_track_t> tracks() const {
+        int n = 0;
+        std::vector<rmr_track_t> out(64);
+        detail::throw_status(rmr_tracker_tracks(handle_, out.data(), 64, &n));
+        out.resize(static_cast<size_t>(std::min(n, 64)));
+        return out;
+    }
+    rmr_tracker_t* handle() const noexcept { return handle_; }
+
+   private:
+    rmr_tracker_t* handle_ = nullptr;
+    std::vector<rmr_robot_t> records_;
+    std::vector<int32_t> state_, id_;
+};
+
 inline std::vector<Robot> runOnce(RobotDetector& detector, Locator& locator, const ImageView& image,
                                   const CloudView& cloud, int max_robots = 64) {
     std::vector<rmr_robot_t> recs(static_cast<size_t>(max_robots));

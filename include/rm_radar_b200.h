@@ -141,6 +141,32 @@ int rmr_locator_search(rmr_locator_t* l, rmr_robot_t* robots, int n_robots);
 int rmr_locator_update_pcd(rmr_locator_t* l, const void* file_bytes, size_t size, int* n_points);
 /* the same parser with the points copied back (tests, tools): xyz = float [capacity][3] on the host */
 int rmr_pcd_parse(const void* file_bytes, size_t size, float* xyz, int capacity, int* n_points, int device);
+/* ---- radar::Tracker — src/track/tracker.h:23-53 (the step after the path) ----
+ * Host code (a <= 20 x 20 assignment and a 9-state Singer EKF per track); it consumes the robot records detect +
+ * locate have just produced.  Tracker::Tracker(observation_noise, class_num, init_thresh = 4, miss_thresh = 10,
+ * max_acceleration = 2, acceleration_correlation_time = 1, distance_weight = 0.4, feature_weight = 0.6,
+ * max_iter = 100, distance_thresh = 0.8) — tracker.cpp:47-60. */
+typedef struct rmr_tracker rmr_tracker_t;
+typedef struct rmr_track {      /* radar::Track, src/track/track.h:27-196 (inspection) */
+    int32_t id, label, state;   /* state: 0 tentative, 1 confirmed */
+    int32_t init_count, miss_count;
+    float location[3];
+    float filter_state[9];      /* x vx ax  y vy ay  z vz az */
+} rmr_track_t;
+int rmr_tracker_create(rmr_tracker_t** out, const float observation_noise[3], int class_num, int init_thresh,
+                       int miss_thresh, float max_acceleration, float acceleration_correlation_time,
+                       float distance_weight, float feature_weight, int max_iter, float distance_thresh);
+void rmr_tracker_destroy(rmr_tracker_t* t);
+/* Tracker::update(std::vector<Robot>&, time_point) — tracker.cpp:126-220.  `robots` is updated in place the way
+ * Robot::setTrack does it (robot.cpp:81-94: a confirmed track overrides label and location, a tentative one fills
+ * what is missing); track_state[i] = -1 not tracked / 0 tentative / 1 confirmed, track_id[i] = id or -1 (both may
+ * be NULL).  timestamp_ns stands for the high_resolution_clock time_point. */
+int rmr_tracker_update(rmr_tracker_t* t, rmr_robot_t* robots, int n, int64_t timestamp_ns, int32_t* track_state,
+                       int32_t* track_id);
+int rmr_tracker_tracks(rmr_tracker_t* t, rmr_track_t* out, int capacity, int* count);
+/* radar::track::auction — src/track/auction.h:33-126 (values [n_agents][n_tasks] row-major -> task per agent, -1) */
+int rmr_auction(const float* values, int n_agents, int n_tasks, int max_iter, int32_t* assignment);
+
 /* ---- JPEG frames ----
  * Replaces cv::imread in front of RobotDetector::detect (samples/main.cpp:24-40): the file image is uploaded as it
  * is (~1/16 of the raw frame) and decoded on the device into the BGR frame the detector reads.  Baseline / extended

@@ -62,6 +62,11 @@ class Robot:
     location: tuple | None = None
     cluster: int | None = None
     cluster_points: int = 0
+    track_state: int | None = None   # 0 tentative, 1 confirmed (robot.h:139-141)
+    track_id: int | None = None
+
+    def isTracked(self) -> bool:    # robot.h:81
+        return self.track_state is not None
 
     def isDetected(self) -> bool:   # robot.h:65
         return self.armors is not None
@@ -420,6 +425,76 @@ def run_once(detector: "RobotDetector", locator: "Locator", image: np.ndarray, c
     recs, n = run_once_records(detector, locator, img.ctypes.data, False, img.shape[1], img.shape[0], img.strides[0],
                                pts.ctypes.data if pts is not None else 0, False, len(pts) if pts is not None else 0, 12)
     return [_robot_from_rec(recs[i]) for i in range(n)]
+
+
+def auction(values, max_iter: int = 100) -> list:
+    """radar::track::auction — auction.h:33-126: value matrix [agents, tasks] -> task per agent (-1 = unmatched)."""
+    lib = _lib.load()
+    v = np.ascontiguousarray(values, np.float32)
+    n_agents = v.shape[0]
+    n_tasks = v.shape[1] if v.ndim == 2 else 0
+    out = (C.c_int32 * max(n_agents, 1))()
+    _lib.check(lib.rmr_auction(v.ctypes.data, n_agents, n_tasks, max_iter, out))
+    return [int(out[i]) for i in range(n_agents)]
+
+
+class Tracker:
+    """radar::Tracker — tracker.h:23-53, tracker.cpp:47-220.  Host code inside the same library."""
+
+    def __init__(self, observation_noise, class_num, init_thresh=4, miss_thresh=10, max_acceleration=2.0,
+                 acceleration_correlation_time=1.0, distance_weight=0.40, feature_weight=0.60, max_iter=100,
+                 distance_thresh=0.8):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        noise = (C.c_float * 3)(*[float(x) for x in observation_noise])
+        _lib.check(self._lib.rmr_tracker_create(C.byref(self._h), noise, class_num, init_thresh, miss_thresh, max_acceleration,
+                                                acceleration_correlation_time, distance_weight, feature_weight, max_iter,
+                                                distance_thresh))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.rmr_tracker_destroy(self._h)
+            self._h.value = None
+
+    def update(self, robots: list, timestamp_ns: int):
+        """Tracker::update(std::vector<Robot>&, time_point): robots are updated in place (Robot::setTrack)."""
+        n = len(robots)
+        recs = (_lib.RobotRec * max(n, 1))()
+        for i, r in enumerate(robots):
+            rec = recs[i]
+            rec.label = -1 if r.label is None else int(r.label)
+            if r.rect is not None:
+                rec.rect = (C.c_float * 4)(*r.rect)
+                rec.has_rect = 1
+            if r.armors is not None:
+                rec.is_detected = 1
+                rec.confidence = float(r.confidence or 0.0)
+                rec.n_armors = min(len(r.armors), _lib.MAX_ARMORS)
+                for k in range(rec.n_armors):
+                    a = r.armors[k]
+                    rec.armors[k] = _lib.Detection(a.x, a.y, a.width, a.height, a.label, a.confidence)
+            if r.location is not None:
+                rec.is_located = 1
+                rec.location = (C.c_float * 3)(*r.location)
+        state = (C.c_int32 * max(n, 1))()
+        tid = (C.c_int32 * max(n, 1))()
+        self.update_records(recs, n, timestamp_ns, state, tid)
+        for i, r in enumerate(robots):
+            if state[i] >= 0:
+                r.track_state, r.track_id = int(state[i]), int(tid[i])
+                r.label = int(recs[i].label)
+                r.location = tuple(recs[i].location)
+
+    def update_records(self, recs, n: int, timestamp_ns: int, state=None, tid=None):
+        """Raw-record variant: the array `rmr_run_once` filled goes straight in."""
+        _lib.check(self._lib.rmr_tracker_update(self._h, recs, n, int(timestamp_ns), state, tid))
+
+    def tracks(self) -> list:
+        n = C.c_int()
+        out = (_lib.TrackRec * 64)()
+        _lib.check(self._lib.rmr_tracker_tracks(self._h, out, 64, C.byref(n)))
+        return [dict(id=t.id, label=t.label, state=t.state, init_count=t.init_count, miss_count=t.miss_count,
+                     location=tuple(t.location), filter_state=tuple(t.filter_state)) for t in out[:min(n.value, 64)]]
 
 
 def jpeg_info(file_bytes: bytes) -> dict:

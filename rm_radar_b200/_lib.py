@@ -26,6 +26,11 @@ class RobotRec(C.Structure):
                 ("cluster", C.c_int32), ("cluster_points", C.c_int32)]
 
 
+class TrackRec(C.Structure):
+    _fields_ = [("id", C.c_int32), ("label", C.c_int32), ("state", C.c_int32), ("init_count", C.c_int32),
+                ("miss_count", C.c_int32), ("location", C.c_float * 3), ("filter_state", C.c_float * 9)]
+
+
 # every symbol include/rm_radar_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "rmr_last_error", "rmr_device_count",
@@ -40,6 +45,7 @@ SYMBOLS = [
     "rmr_locator_cluster", "rmr_locator_search", "rmr_locator_update_pcd", "rmr_pcd_parse", "rmr_locator_load_background", "rmr_locator_set_stream", "rmr_locator_image_size",
     "rmr_locator_read_image", "rmr_locator_stats", "rmr_locator_read_foreground",
     "rmr_run_once", "rmr_conv_selftest", "rmr_conv_timeline",
+    "rmr_tracker_create", "rmr_tracker_destroy", "rmr_tracker_update", "rmr_tracker_tracks", "rmr_auction",
     "rmr_jpeg_decoder_create", "rmr_jpeg_decoder_destroy", "rmr_jpeg_decoder_set_stream", "rmr_jpeg_info", "rmr_jpeg_decode",
     "rmr_jpeg_decode_device", "rmr_jpeg_decoder_status", "rmr_jpeg_decoder_read_coefficients", "rmr_jpeg_decoder_profile", "rmr_robot_detector_detect_jpeg",
 ]
@@ -100,6 +106,12 @@ def load():
     lib.rmr_locator_search.argtypes = [vp, P(RobotRec), ci]
     lib.rmr_locator_update_pcd.argtypes = [vp, vp, C.c_size_t, P(ci)]
     lib.rmr_pcd_parse.argtypes = [vp, C.c_size_t, vp, ci, P(ci), ci]
+    lib.rmr_tracker_create.argtypes = [P(vp), P(cf), ci, ci, ci, cf, cf, cf, cf, ci, cf]
+    lib.rmr_tracker_destroy.argtypes = [vp]
+    lib.rmr_tracker_destroy.restype = None
+    lib.rmr_tracker_update.argtypes = [vp, vp, ci, C.c_int64, P(C.c_int32), P(C.c_int32)]
+    lib.rmr_tracker_tracks.argtypes = [vp, vp, ci, P(ci)]
+    lib.rmr_auction.argtypes = [vp, ci, ci, ci, P(C.c_int32)]
     lib.rmr_jpeg_decoder_create.argtypes = [P(vp), ci]
     lib.rmr_jpeg_decoder_destroy.argtypes = [vp]
     lib.rmr_jpeg_decoder_destroy.restype = None

@@ -9,6 +9,7 @@
 #include "locate.h"
 #include "jpeg.h"
 #include "pcd.h"
+#include "track.h"
 
 using namespace rmr;
 
@@ -20,6 +21,9 @@ struct rmr_robot_detector {
     std::unique_ptr<RobotDetector> impl;
     rmr_detector car_view, armor_view;
     int last_cars = 0;
+};
+struct rmr_tracker {
+    std::unique_ptr<Tracker> impl;
 };
 struct rmr_jpeg_decoder {
     std::unique_ptr<JpegDecoder> impl;
@@ -368,6 +372,51 @@ int rmr_pcd_parse(const void* file_bytes, size_t size, float* xyz, int capacity,
         }
         cudaStreamDestroy(s);
         cudaFree(dev);
+    });
+}
+int rmr_tracker_create(rmr_tracker_t** out, const float observation_noise[3], int class_num, int init_thresh,
+                       int miss_thresh, float max_acceleration, float acceleration_correlation_time,
+                       float distance_weight, float feature_weight, int max_iter, float distance_thresh) {
+    return guarded([&] {
+        if (!out) throw std::invalid_argument("null argument");
+        auto h = std::make_unique<rmr_tracker>();
+        h->impl = std::make_unique<Tracker>(observation_noise, class_num, init_thresh, miss_thresh, max_acceleration,
+                                            acceleration_correlation_time, distance_weight, feature_weight, max_iter,
+                                            distance_thresh);
+        *out = h.release();
+    });
+}
+void rmr_tracker_destroy(rmr_tracker_t* t) { delete t; }
+int rmr_tracker_update(rmr_tracker_t* t, rmr_robot_t* robots, int n, int64_t timestamp_ns, int32_t* track_state,
+                       int32_t* track_id) {
+    return guarded([&] {
+        if (!t) throw std::invalid_argument("null argument");
+        t->impl->update(robots, n, timestamp_ns, track_state, track_id);
+    });
+}
+int rmr_tracker_tracks(rmr_tracker_t* t, rmr_track_t* out, int capacity, int* count) {
+    return guarded([&] {
+        if (!t || !count) throw std::invalid_argument("null argument");
+        const std::vector<TrackInfo> tr = t->impl->tracks();
+        *count = static_cast<int>(tr.size());
+        for (int i = 0; i < *count && i < capacity && out; ++i) {
+            out[i].id = tr[i].id;
+            out[i].label = tr[i].label;
+            out[i].state = tr[i].state;
+            out[i].init_count = tr[i].init_count;
+            out[i].miss_count = tr[i].miss_count;
+            std::memcpy(out[i].location, tr[i].location, sizeof(out[i].location));
+            std::memcpy(out[i].filter_state, tr[i].filter_state, sizeof(out[i].filter_state));
+        }
+    });
+}
+int rmr_auction(const float* values, int n_agents, int n_tasks, int max_iter, int32_t* assignment) {
+    return guarded([&] {
+        if (n_agents < 0 || n_tasks < 0 || (n_agents > 0 && !assignment) || (n_agents * n_tasks > 0 && !values))
+            throw std::invalid_argument("bad argument");
+        const std::vector<float> v(values, values + static_cast<size_t>(n_agents) * n_tasks);
+        const std::vector<int> a = auction(v, n_agents, n_tasks, max_iter);
+        for (int i = 0; i < n_agents; ++i) assignment[i] = a[i];
     });
 }
 int rmr_jpeg_decoder_create(rmr_jpeg_decoder_t** out, int device) {
