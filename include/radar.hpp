@@ -535,4 +535,13 @@ inline std::vector<Robot> runOnce(RobotDetector& detector, Locator& locator, con
     return robots;
 }
 
+// SampleRadar::runOnce as the sample writes it, tracker included (sample_radar.h:106-127)
+inline std::vector<Robot> runOnce(RobotDetector& detector, Locator& locator, Tracker& tracker, const ImageView& image,
+                                  const CloudView& cloud, const std::chrono::high_resolution_clock::time_point& timestamp,
+                                  int max_robots = 64) {
+    std::vector<Robot> robots = runOnce(detector, locator, image, cloud, max_robots);
+    tracker.update(robots, timestamp);
+    return robots;
+}
+
 }  // namespace radar

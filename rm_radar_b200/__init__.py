@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import enum
 import os
+import time
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -418,13 +419,24 @@ def run_once_records(detector: "RobotDetector", locator: "Locator", frame_ptr: i
     return detector._recs, min(n.value, detector.max_cars)
 
 
-def run_once(detector: "RobotDetector", locator: "Locator", image: np.ndarray, cloud) -> list:
-    """One frame of the whole path on host arrays: detect + update + cluster + search -> list[Robot]."""
+def run_once(detector: "RobotDetector", locator: "Locator", image: np.ndarray, cloud, tracker: "Tracker | None" = None,
+             timestamp_ns: int | None = None) -> list:
+    """One frame of the whole path on host arrays: detect + update + cluster + search (+ Tracker::update when a
+    tracker is given, sample_radar.h:121-123) -> list[Robot]."""
     img = _as_bgr(image)
     pts = np.ascontiguousarray(np.asarray(cloud, np.float32)[:, :3]) if cloud is not None and len(cloud) else None
     recs, n = run_once_records(detector, locator, img.ctypes.data, False, img.shape[1], img.shape[0], img.strides[0],
                                pts.ctypes.data if pts is not None else 0, False, len(pts) if pts is not None else 0, 12)
-    return [_robot_from_rec(recs[i]) for i in range(n)]
+    if tracker is None:
+        return [_robot_from_rec(recs[i]) for i in range(n)]
+    state, tid = (C.c_int32 * max(n, 1))(), (C.c_int32 * max(n, 1))()
+    tracker.update_records(recs, n, timestamp_ns if timestamp_ns is not None else time.monotonic_ns(), state, tid)
+    robots = [_robot_from_rec(recs[i]) for i in range(n)]
+    for i, r in enumerate(robots):
+        if state[i] >= 0:
+            r.track_state, r.track_id = int(state[i]), int(tid[i])
+            r.label = int(recs[i].label)        # a tracked, undetected robot carries the track's label
+    return robots
 
 
 def auction(values, max_iter: int = 100) -> list:

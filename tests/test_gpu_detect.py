@@ -189,3 +189,41 @@ def test_run_once_equals_separate_calls():
         for g, w in zip(got, want):
             assert g.rect == w.rect and g.label == w.label and g.confidence == w.confidence
             assert g.location == w.location and g.cluster == w.cluster
+
+
+@needs_models
+def test_whole_chain_jpeg_detect_locate_track():
+    """SampleRadar::runOnce end to end (sample_radar.h:106-127): JPEG in, tracked robots out, over repeated frames."""
+    from oracle import track_oracle as to
+    clouds = fx.load_clouds()
+    det = rr.RobotDetector(fx.engine("car"), fx.engine("armor"), fx.IMAGE_SIZE, fx.CLASS_NUM, fx.MAX_BATCH, fx.OPT_BATCH)
+    loc = rr.Locator(fx.IMAGE_SIZE[0], fx.IMAGE_SIZE[1], fx.INTRINSIC, fx.LIDAR_TO_CAMERA, fx.WORLD_TO_CAMERA)
+    dec = rr.JpegDecoder(0)
+    trk = rr.Tracker([0.2, 0.2, 0.2], fx.CLASS_NUM)
+    ora = to.Tracker([0.2, 0.2, 0.2], fx.CLASS_NUM)
+    loc.update(clouds["background"])
+    jpg = open(os.path.join(fx.GOLDEN, "frames", "0.jpg"), "rb").read()
+    img = dec.decode(jpg)
+    t = 0
+    import copy
+    for frame in range(6):
+        t += 40_000_000
+        plain = rr.run_once(det, loc, img, clouds["c0"])          # the observation of this frame
+        obs = [to.RobotObs(armors=[(a.label, a.confidence) for a in r.armors] if r.armors is not None else None,
+                           location=r.location, label=r.label) for r in plain]
+        robots = copy.deepcopy(plain)
+        trk.update(robots, t)
+        ora.update(obs, t)
+        assert [r.track_state for r in robots] == [o.track_state for o in obs]
+        assert [r.label for r in robots] == [o.label for o in obs]
+        for r, o in zip(robots, obs):
+            if o.location is not None:
+                assert np.allclose(r.location, o.location, atol=1e-3)
+    located = [r for r in robots if r.isDetected() and r.isLocated()]
+    assert located and all(r.track_state == 1 for r in located)   # confirmed after init_thresh = 4 frames
+    assert len(trk.tracks()) == len(ora.tracks) > 0
+    # the fused entry point with the tracker attached: same tracks keep being matched
+    t += 40_000_000
+    fused = rr.run_once(det, loc, img, clouds["c0"], tracker=trk, timestamp_ns=t)
+    assert len(fused) == len(robots)
+    assert [r.track_id for r in fused if r.isDetected() and r.isLocated()] == [r.track_id for r in located]
