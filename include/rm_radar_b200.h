@@ -171,7 +171,8 @@ int rmr_auction(const float* values, int n_agents, int n_tasks, int max_iter, in
  * Replaces cv::imread in front of RobotDetector::detect (samples/main.cpp:24-40): the file image is uploaded as it
  * is (~1/16 of the raw frame) and decoded on the device into the BGR frame the detector reads.  Baseline / extended
  * sequential Huffman JPEG, 8 bit, grayscale or YCbCr 4:4:4 / 4:2:2 / 4:2:0, with or without restart markers;
- * anything else fails with RMR_ERR_INVALID_ARGUMENT.  Output is bit-identical to libjpeg-turbo's default decode
+ * anything else -- and files whose EXIF orientation or RGB coding would make cv::imread return something else than
+ * the plain decode -- fails with RMR_ERR_INVALID_ARGUMENT.  Output is bit-identical to libjpeg-turbo's default decode
  * (JDCT_ISLOW, fancy upsampling), i.e. to what cv::imread returns. */
 typedef struct rmr_jpeg_decoder rmr_jpeg_decoder_t;
 int rmr_jpeg_decoder_create(rmr_jpeg_decoder_t** out, int device);

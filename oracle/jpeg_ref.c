@@ -38,6 +38,10 @@ typedef struct {
     int qdef[4];
     Huff dc[4], ac[4];
     int restart;
+    int comp_id[3];
+    int adobe_transform;   /* -1: no APP14 Adobe marker */
+    int orientation;       /* EXIF tag 0x0112, 0 if absent */
+    int jfif;              /* APP0 JFIF marker seen: YCbCr by definition */
     const uint8_t* scan;
     size_t scan_len;
 } Jpeg;
@@ -60,6 +64,7 @@ static int build_huff(Huff* t) {
 
 static int parse(const uint8_t* d, size_t n, Jpeg* j) {
     memset(j, 0, sizeof(*j));
+    j->adobe_transform = -1;
     if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return JE_CORRUPT;
     size_t i = 2;
     int have_sof = 0;
@@ -114,6 +119,7 @@ static int parse(const uint8_t* d, size_t n, Jpeg* j) {
             if (j->ncomp != 1 && j->ncomp != 3) return JE_UNSUPPORTED;
             if (pl < (size_t)(6 + 3 * j->ncomp) || j->w == 0 || j->h == 0) return JE_CORRUPT;
             for (int c = 0; c < j->ncomp; ++c) {
+                j->comp_id[c] = p[6 + 3 * c];
                 j->hs[c] = p[7 + 3 * c] >> 4;
                 j->vs[c] = p[7 + 3 * c] & 15;
                 j->tq[c] = p[8 + 3 * c];
@@ -122,6 +128,31 @@ static int parse(const uint8_t* d, size_t n, Jpeg* j) {
             have_sof = 1;
         } else if (m >= 0xC2 && m <= 0xCF && m != 0xC8 && m != 0xCC) {
             return JE_UNSUPPORTED;   /* progressive, lossless, arithmetic */
+        } else if (m == 0xE1) {   /* EXIF orientation: cv::imread rotates / mirrors the decoded frame for values 2..8 */
+            if (pl >= 14 && memcmp(p, "Exif\0\0", 6) == 0) {
+                const uint8_t* t = p + 6;
+                const size_t tn = pl - 6;
+                const int le = t[0] == 'I' && t[1] == 'I', be = t[0] == 'M' && t[1] == 'M';
+#define U16(o) (le ? (t[o] | (t[(o) + 1] << 8)) : ((t[o] << 8) | t[(o) + 1]))
+#define U32(o) (le ? ((size_t)t[o] | ((size_t)t[(o) + 1] << 8) | ((size_t)t[(o) + 2] << 16) | ((size_t)t[(o) + 3] << 24)) \
+                   : (((size_t)t[o] << 24) | ((size_t)t[(o) + 1] << 16) | ((size_t)t[(o) + 2] << 8) | (size_t)t[(o) + 3]))
+                if ((le || be) && U16(2) == 42) {
+                    const size_t ifd = U32(4);
+                    if (ifd + 2 <= tn) {
+                        const int entries = U16(ifd);
+                        for (int e = 0; e < entries && ifd + 2 + (size_t)(e + 1) * 12 <= tn; ++e) {
+                            const size_t o = ifd + 2 + (size_t)e * 12;
+                            if (U16(o) == 0x0112) j->orientation = U16(o + 8);
+                        }
+                    }
+                }
+#undef U16
+#undef U32
+            }
+        } else if (m == 0xE0) {
+            if (pl >= 5 && memcmp(p, "JFIF", 5) == 0) j->jfif = 1;
+        } else if (m == 0xEE) {
+            if (pl >= 12 && memcmp(p, "Adobe", 5) == 0) j->adobe_transform = p[11];
         } else if (m == 0xDD) {
             if (pl < 2) return JE_CORRUPT;
             j->restart = (p[0] << 8) | p[1];
@@ -148,6 +179,10 @@ static int parse(const uint8_t* d, size_t n, Jpeg* j) {
     }
     for (int c = 0; c < j->ncomp; ++c)
         if (!j->qdef[j->tq[c]] || !j->dc[j->td[c]].defined || !j->ac[j->ta[c]].defined) return JE_CORRUPT;
+    if (j->orientation > 1 && j->orientation <= 8) return JE_UNSUPPORTED;        /* cv::imread would rotate */
+    if (j->ncomp == 3 && !j->jfif && (j->adobe_transform == 0 ||                  /* RGB-coded, no YCbCr transform */
+                          (j->adobe_transform < 0 && j->comp_id[0] == 'R' && j->comp_id[1] == 'G' && j->comp_id[2] == 'B')))
+        return JE_UNSUPPORTED;
     return JE_OK;
 }
 

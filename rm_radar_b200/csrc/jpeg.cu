@@ -989,6 +989,7 @@ JpegHeader jpeg_parse_header(const void* file, size_t size) {
                 if (n < static_cast<size_t>(6 + 3 * h.components) || h.width == 0 || h.height == 0) bad("bad SOF segment");
                 int hs[3] = {1, 1, 1}, vs[3] = {1, 1, 1};
                 for (int c = 0; c < h.components; ++c) {
+                    h.component_id[c] = p[6 + 3 * c];
                     hs[c] = p[7 + 3 * c] >> 4;
                     vs[c] = p[7 + 3 * c] & 15;
                     h.quant_of[c] = p[8 + 3 * c];
@@ -1023,6 +1024,42 @@ JpegHeader jpeg_parse_header(const void* file, size_t size) {
                 have_scan = true;
                 break;
             }
+            case 0xE1: {   // APP1: cv::imread applies the EXIF orientation (it rotates / mirrors the frame); only "normal" is accepted
+                if (n >= 14 && std::memcmp(p, "Exif\0\0", 6) == 0) {
+                    const uint8_t* t = p + 6;
+                    const size_t tn = n - 6;
+                    const bool le = t[0] == 'I' && t[1] == 'I', be = t[0] == 'M' && t[1] == 'M';
+                    auto u16 = [&](size_t o) { return le ? t[o] | (t[o + 1] << 8) : (t[o] << 8) | t[o + 1]; };
+                    auto u32 = [&](size_t o) {
+                        return le ? static_cast<size_t>(t[o]) | (static_cast<size_t>(t[o + 1]) << 8) | (static_cast<size_t>(t[o + 2]) << 16) |
+                                        (static_cast<size_t>(t[o + 3]) << 24)
+                                  : (static_cast<size_t>(t[o]) << 24) | (static_cast<size_t>(t[o + 1]) << 16) |
+                                        (static_cast<size_t>(t[o + 2]) << 8) | static_cast<size_t>(t[o + 3]);
+                    };
+                    if ((le || be) && u16(2) == 42) {
+                        const size_t ifd = u32(4);
+                        if (ifd + 2 <= tn) {
+                            const int entries = u16(ifd);
+                            for (int e = 0; e < entries && ifd + 2 + static_cast<size_t>(e + 1) * 12 <= tn; ++e) {
+                                const size_t o = ifd + 2 + static_cast<size_t>(e) * 12;
+                                if (u16(o) == 0x0112) {
+                                    const int orientation = u16(o + 8);
+                                    if (orientation > 1 && orientation <= 8)
+                                        bad("EXIF orientation " + std::to_string(orientation) +
+                                            " is not supported (cv::imread would rotate or mirror this frame)");
+                                }
+                            }
+                        }
+                    }
+                }
+                break;
+            }
+            case 0xE0:     // APP0 "JFIF": three components are YCbCr by definition
+                if (n >= 5 && std::memcmp(p, "JFIF", 5) == 0) h.jfif = true;
+                break;
+            case 0xEE:     // APP14 "Adobe": without JFIF, transform 0 on three components means the samples are RGB
+                if (n >= 12 && std::memcmp(p, "Adobe", 5) == 0) h.adobe_transform = p[11];
+                break;
             default:
                 if (m >= 0xC2 && m <= 0xCF && m != 0xC8 && m != 0xCC)
                     bad("only baseline / extended sequential Huffman JPEG is supported (this file is progressive, lossless or arithmetic)");
@@ -1032,6 +1069,12 @@ JpegHeader jpeg_parse_header(const void* file, size_t size) {
     }
     for (int c = 0; c < h.components; ++c)
         if (!h.have_quant[h.quant_of[c]] || !h.have_huff[0][h.dc_of[c]] || !h.have_huff[1][h.ac_of[c]]) bad("missing table");
+    // libjpeg's colour-space guess (jdapimin.c default_decompress_parms): JFIF means YCbCr; otherwise an Adobe marker with
+    // transform 0 means RGB; with neither marker, component ids that spell "RGB" mean RGB
+    if (h.components == 3 && !h.jfif &&
+        (h.adobe_transform == 0 ||
+         (h.adobe_transform < 0 && h.component_id[0] == 'R' && h.component_id[1] == 'G' && h.component_id[2] == 'B')))
+        bad("RGB-coded JPEG (no YCbCr transform) is not supported");
     // the entropy-coded segment ends at EOI: the last FF D9 of the file
     size_t end = size;
     while (end >= h.scan_offset + 2 && !(d[end - 2] == 0xFF && d[end - 1] == 0xD9)) --end;

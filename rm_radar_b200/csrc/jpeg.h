@@ -11,6 +11,9 @@ struct JpegHeader {
     int width = 0, height = 0, components = 0;
     int h_samp = 1, v_samp = 1;          // luma sampling factors (chroma is 1x1)
     int restart_interval = 0;            // MCUs per restart interval, 0 = none
+    int component_id[3] = {0, 0, 0};
+    int adobe_transform = -1;            // APP14 transform byte, -1 = no Adobe marker
+    bool jfif = false;                   // APP0 JFIF marker seen
     int quant_of[3] = {0, 0, 0}, dc_of[3] = {0, 0, 0}, ac_of[3] = {0, 0, 0};
     uint16_t quant[4][64] = {};          // natural (row-major) order
     uint8_t bits[2][4][17] = {};         // [dc/ac][table id][code length] counts

@@ -83,3 +83,29 @@ def test_headers_compile_standalone(tmp_path):
     cpp = tmp_path / "t.cpp"
     cpp.write_text('#include "radar.hpp"\nint main(){ radar::Robot r; return r.isDetected() || r.isLocated(); }\n')
     subprocess.check_call(["g++", "-std=c++20", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I" + inc, str(cpp)])
+
+
+def test_jpeg_header_parser_scope_matches_the_oracle():
+    """Host-side half of the JPEG stage (no GPU): rmr_jpeg_info accepts and rejects exactly what the oracle does,
+    including the metadata that changes what cv::imread returns (EXIF orientation, RGB-coded files)."""
+    import glob
+
+    import numpy as np
+
+    import rm_radar_b200 as rr
+    from oracle import jpeg_oracle as jo
+    from tests.test_oracle_jpeg import JPEG_DIR, metadata_cases
+    for path in sorted(glob.glob(os.path.join(JPEG_DIR, "*.jpg"))):
+        data = open(path, "rb").read()
+        assert rr.jpeg_info(data) == jo.info(data), path
+    for name, data, ok in metadata_cases():
+        if ok:
+            assert rr.jpeg_info(data) == jo.info(data), name
+        else:
+            with pytest.raises(ValueError):
+                rr.jpeg_info(data)
+            with pytest.raises(ValueError):
+                jo.info(data)
+    for bad in (b"", b"\xff\xd8", b"not a jpeg", open(os.path.join(JPEG_DIR, "photo_420_q90.jpg"), "rb").read()[:100]):
+        with pytest.raises(ValueError):
+            rr.jpeg_info(bad)

@@ -124,6 +124,18 @@ def test_rejects_unsupported_and_flags_corrupt_streams(decoder):
     check(decoder, good, jo.decode(good), "after errors")
 
 
+def test_metadata_segments(decoder):
+    """EXIF orientation 1 / JFIF-beside-Adobe / comments decode like the plain file; rotated or RGB-coded files raise."""
+    from tests.test_oracle_jpeg import metadata_cases
+    plain = jo.decode(open(os.path.join(JPEG_DIR, "photo_420_q90.jpg"), "rb").read())
+    for name, data, ok in metadata_cases():
+        if ok:
+            check(decoder, data, plain, name)
+        else:
+            with pytest.raises(ValueError):
+                decoder.decode(data)
+
+
 def test_result_does_not_depend_on_the_subsequence_size():
     """The fixed point of the synchronisation is the sequential decode whatever the cut (jpeg.cu header)."""
     code = (

@@ -90,3 +90,49 @@ def test_oracle_rejects_what_it_does_not_decode():
         jo.decode(good[:200])
     with pytest.raises(ValueError):
         jo.decode(b"not a jpeg at all")
+
+
+def _insert_segment(jpeg: bytes, marker: int, payload: bytes) -> bytes:
+    """A marker segment placed right after SOI."""
+    seg = bytes([0xFF, marker]) + (len(payload) + 2).to_bytes(2, "big") + payload
+    return jpeg[:2] + seg + jpeg[2:]
+
+
+def exif_orientation(value: int, little_endian: bool = True) -> bytes:
+    bo = "little" if little_endian else "big"
+    tiff = (b"II" if little_endian else b"MM") + (42).to_bytes(2, bo) + (8).to_bytes(4, bo)
+    entry = (0x0112).to_bytes(2, bo) + (3).to_bytes(2, bo) + (1).to_bytes(4, bo) + value.to_bytes(2, bo) + b"\x00\x00"
+    return b"Exif\x00\x00" + tiff + (1).to_bytes(2, bo) + entry + (0).to_bytes(4, bo)
+
+
+def metadata_cases():
+    """(name, file, decodes_like_the_plain_file) for the metadata that changes what cv::imread returns."""
+    good = open(os.path.join(JPEG_DIR, "photo_420_q90.jpg"), "rb").read()
+    yield "exif orientation 1", _insert_segment(good, 0xE1, exif_orientation(1)), True
+    yield "exif orientation 1 big endian", _insert_segment(good, 0xE1, exif_orientation(1, False)), True
+    yield "exif orientation 6", _insert_segment(good, 0xE1, exif_orientation(6)), False
+    yield "exif orientation 3 big endian", _insert_segment(good, 0xE1, exif_orientation(3, False)), False
+    yield "adobe transform 1", _insert_segment(good, 0xEE, b"Adobe\x00\x64\x00\x00\x00\x00\x01"), True
+    yield "adobe transform 0 beside JFIF (JFIF wins)", _insert_segment(good, 0xEE, b"Adobe\x00\x64\x00\x00\x00\x00\x00"), True
+    assert good[2:4] == b"\xff\xe0" and good[6:10] == b"JFIF"
+    no_jfif = good[:2] + good[4 + int.from_bytes(good[4:6], "big"):]
+    yield "no JFIF, no Adobe (component ids 1 2 3)", no_jfif, True
+    yield "adobe transform 0 without JFIF (RGB)", _insert_segment(no_jfif, 0xEE, b"Adobe\x00\x64\x00\x00\x00\x00\x00"), False
+    yield "comment", _insert_segment(good, 0xFE, b"hello"), True
+
+
+def test_metadata_that_changes_the_reference_output_is_rejected():
+    """cv::imread rotates by the EXIF orientation and skips the colour transform for RGB-coded files: both are outside
+    the decoder's scope and must fail loudly instead of returning other pixels than the reference would."""
+    cv2 = pytest.importorskip("cv2")
+    good = open(os.path.join(JPEG_DIR, "photo_420_q90.jpg"), "rb").read()
+    plain = jo.decode(good)
+    for name, data, same in metadata_cases():
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        if same:
+            assert np.array_equal(ref, plain), name                     # the reference is unaffected by this segment
+            assert np.array_equal(jo.decode(data), plain), name
+        else:
+            assert ref is None or ref.shape != plain.shape or not np.array_equal(ref, plain), name   # the reference differs
+            with pytest.raises(ValueError):
+                jo.decode(data)
