@@ -75,6 +75,7 @@ struct JpegDev {
     uint2* cand;
     uint4* res;
     unsigned char* bmap;
+    uint4* ck;                    // [n_sub][kLanes][kCheckpoints]: (bit position, zig-zag | block << 8, blocks so far)
     unsigned long long* tstamp;   // phase boundaries of the entropy kernel (block 0), globaltimer ns
     int n_sub;
     uint32_t sub_bits;
@@ -255,13 +256,21 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     return v;
 }
 
-template <bool kWrite>
+// kCk: the state at the first code boundary at or after ck_next, ck_next + ck_step, ... (kCheckpoints of them) is recorded
+// with the blocks completed so far, so that the write pass can split the subsequence over the lanes of its group.
+constexpr int kCheckpoints = 8;
+template <bool kWrite, bool kCk = false>
 __device__ __forceinline__ uint2 decode_range(const JpegDev& J, const SmemTables& T, uint2 st, uint32_t limit, int& n_done,
-                                              long blk0) {
+                                              long blk0, uint4* ck_out = nullptr, uint32_t ck_next = 0, uint32_t ck_step = 0) {
     const uint32_t* words = reinterpret_cast<const uint32_t*>(J.stream);
     uint32_t p = st.x;
     int z = st.y & 0xFF, c = st.y >> 8;
-    if (p >= limit) return st;
+    int ckj = 0;
+    if (p >= limit) {
+        if (kCk)
+            for (; ckj < kCheckpoints; ++ckj) __stcg(ck_out + ckj, make_uint4(p, st.y, 0u, 0u));
+        return st;
+    }
     int k = 0;
     if (J.n_intervals > 1) {   // the restart interval p lies in
         int lo = 0, hi = J.n_intervals - 1;
@@ -292,6 +301,14 @@ __device__ __forceinline__ uint2 decode_range(const JpegDev& J, const SmemTables
     uint32_t lut2_base = smem_u32(&T.lut2[0][0]);
     asm volatile("" : "+r"(lut2_base));
     while (p < limit) {
+        if (kCk) {
+            while (ckj < kCheckpoints && p >= ck_next) {
+                __stcg(ck_out + ckj, make_uint4(p, static_cast<uint32_t>(z) | (static_cast<uint32_t>(c) << 8),
+                                                static_cast<uint32_t>(n_done), 0u));
+                ++ckj;
+                ck_next += ck_step;
+            }
+        }
         uint32_t off = p - (wi << 5);
         if (off >= 32) {               // at most one word per symbol (a symbol is <= 31 bits); jumps reload below
             ++wi;
@@ -361,6 +378,9 @@ __device__ __forceinline__ uint2 decode_range(const JpegDev& J, const SmemTables
             }
         }
     }
+    if (kCk)      // checkpoints the subsequence ended before: empty tails
+        for (; ckj < kCheckpoints; ++ckj)
+            __stcg(ck_out + ckj, make_uint4(p, static_cast<uint32_t>(z) | (static_cast<uint32_t>(c) << 8), static_cast<uint32_t>(n_done), 0u));
     return make_uint2(p, static_cast<uint32_t>(z) | (static_cast<uint32_t>(c) << 8));
 }
 
@@ -527,7 +547,8 @@ __global__ void __launch_bounds__(kHypThreads) jpeg_entropy_kernel(JpegDev J) {
         uint2 x = make_uint2(kInvalid, kInvalid);
         int n = 0;
         if (in.x != kInvalid) {
-            x = decode_range<false>(J, T, in, hi, n, 0);
+            x = decode_range<false, true>(J, T, in, hi, n, 0, J.ck + (static_cast<size_t>(i) * kLanes + lane) * kCheckpoints, lo,
+                                          J.sub_bits / kCheckpoints);
             if (i + 1 < n_sub) {
                 for (int k = 0; k < J.bpm; ++k) {
                     const uint2 c = __ldcg(cand + static_cast<size_t>(i + 1) * kLanes + k);
@@ -581,7 +602,7 @@ __global__ void __launch_bounds__(kHypThreads) jpeg_entropy_kernel(JpegDev J) {
 
     // ---- seed the fixed-point loop with the chased triples ----
     uint2 my_in = make_uint2(kInvalid, kInvalid), my_out = make_uint2(kInvalid, kInvalid);
-    int my_n = 0;
+    int my_n = 0, my_slot = -1;       // my_slot: whose checkpoints describe the decode from my_in (lane k of pass 1, 6 = my own)
     const int stride = J.n_sub + 1;
     if (owner) {
         const unsigned sel = s_sel[sub] & 7u;
@@ -591,6 +612,7 @@ __global__ void __launch_bounds__(kHypThreads) jpeg_entropy_kernel(JpegDev J) {
             my_in = c;
             my_out = make_uint2(r.x, r.y);
             my_n = static_cast<int>(r.z);
+            my_slot = static_cast<int>(sel);
         }
         __stcg(J.states + stride + i + 1, my_out);       // read as `cur` by round 1
     }
@@ -614,13 +636,16 @@ __global__ void __launch_bounds__(kHypThreads) jpeg_entropy_kernel(JpegDev J) {
                             const uint4 r = __ldcg(res + static_cast<size_t>(i) * kLanes + k);
                             my_out = make_uint2(r.x, r.y);
                             my_n = static_cast<int>(r.z);
+                            my_slot = k;
                             found = true;
                         }
                     }
                 }
                 if (!found) {
                     my_n = 0;
-                    my_out = decode_range<false>(J, T, in, hi, my_n, 0);
+                    my_slot = 6;
+                    my_out = decode_range<false, true>(J, T, in, hi, my_n, 0, J.ck + (static_cast<size_t>(i) * kLanes + 6) * kCheckpoints,
+                                                       lo, J.sub_bits / kCheckpoints);
                     ++decodes;
                 }
             }
@@ -663,17 +688,29 @@ __global__ void __launch_bounds__(kHypThreads) jpeg_entropy_kernel(JpegDev J) {
         s_before[0] = t;
     }
     __syncthreads();
-    if (owner) {
-        const long blk0 = s_before[0] + s_scan[threadIdx.x] - my_n;
+    // write pass: the 8 lanes of a subsequence each take the stretch between two checkpoints of the decode the owner settled on
+    const int blk0 = owner ? static_cast<int>(s_before[0] + s_scan[threadIdx.x] - my_n) : 0;
+    const int group_leader = static_cast<int>(threadIdx.x & 31u & ~7u);
+    const int g_blk0 = __shfl_sync(0xffffffffu, blk0, group_leader);
+    const int g_slot = __shfl_sync(0xffffffffu, my_slot, group_leader);
+    const uint32_t g_in_x = __shfl_sync(0xffffffffu, my_in.x, group_leader), g_in_y = __shfl_sync(0xffffffffu, my_in.y, group_leader);
+    if (active) {
         int n2 = 0;
-        decode_range<true>(J, T, my_in, hi, n2, blk0);
-        if (i == n_sub - 1) {
-            const long total = blk0 + my_n;
-            J.ctrl[CTRL_BLOCKS] = static_cast<int>(total);
-            J.ctrl[CTRL_ROUNDS] = round;
-            if (total != J.n_blocks) atomicOr(&J.ctrl[CTRL_STATUS], ST_BLOCK_COUNT);
-            if (my_out.y != 0) atomicOr(&J.ctrl[CTRL_STATUS], ST_TAIL);
+        if (g_slot >= 0) {
+            const uint4* ck = J.ck + (static_cast<size_t>(i) * kLanes + g_slot) * kCheckpoints;
+            const uint4 from = __ldcg(ck + lane);
+            const uint32_t until = lane + 1 < kCheckpoints ? __ldcg(ck + lane + 1).x : hi;
+            decode_range<true>(J, T, make_uint2(from.x, from.y), min(until, hi), n2, static_cast<long>(g_blk0) + from.z);
+        } else if (lane == 0) {     // no checkpoints (cannot happen once the loop has settled; kept as the plain path)
+            decode_range<true>(J, T, make_uint2(g_in_x, g_in_y), hi, n2, g_blk0);
         }
+    }
+    if (owner && i == n_sub - 1) {
+        const long total = static_cast<long>(blk0) + my_n;
+        J.ctrl[CTRL_BLOCKS] = static_cast<int>(total);
+        J.ctrl[CTRL_ROUNDS] = round;
+        if (total != J.n_blocks) atomicOr(&J.ctrl[CTRL_STATUS], ST_BLOCK_COUNT);
+        if (my_out.y != 0) atomicOr(&J.ctrl[CTRL_STATUS], ST_TAIL);
     }
     __syncthreads();
     stamp(J, 6);
@@ -1139,6 +1176,7 @@ JpegDecoder::~JpegDecoder() {
     cudaFree(states_);
     cudaFree(cand_);
     cudaFree(res_);
+    cudaFree(ck_);
     cudaFree(bmap_);
     cudaFree(tstamp_);
     cudaFree(changed_);
@@ -1180,6 +1218,7 @@ void JpegDecoder::reserve(const JpegHeader& h) {
         regrow(states_, 2 * static_cast<size_t>(cap_sub_ + 1));
         regrow(cand_, static_cast<size_t>(cap_sub_ + 1) * kLanes);
         regrow(res_, static_cast<size_t>(cap_sub_) * kLanes);
+        regrow(ck_, static_cast<size_t>(cap_sub_) * kLanes * kCheckpoints);
         regrow(changed_, static_cast<size_t>(CTRL_CHANGED + cap_sub_ + kMaxRoundsSlack + max_coresident_ + 64));
     }
     if (h.n_blocks > cap_blocks_) {
@@ -1269,6 +1308,7 @@ const uint8_t* JpegDecoder::decode(const void* file, size_t size, uint8_t* dev_b
     J.cand = cand_;
     J.res = res_;
     J.bmap = bmap_;
+    J.ck = ck_;
     J.tstamp = tstamp_;
     J.ctrl = changed_;
     J.grid_sums = changed_ + CTRL_CHANGED + cap_sub_ + kMaxRoundsSlack;

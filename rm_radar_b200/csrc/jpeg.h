@@ -76,6 +76,7 @@ private:
     uint2* states_ = nullptr;           // [2][n_sub + 1]
     uint2* cand_ = nullptr;             // [n_sub + 1][8] candidate states per subsequence boundary
     uint4* res_ = nullptr;              // [n_sub][8] decode results from each candidate
+    uint4* ck_ = nullptr;               // [n_sub][8][8] checkpoints inside each of those decodes (write pass split)
     unsigned char* bmap_ = nullptr;     // per-block lane maps of the link chase
     unsigned long long* tstamp_ = nullptr;
     bool simple_ = false;               // RMR_JPEG_SIMPLE=1: single-hypothesis kernel
