@@ -58,9 +58,6 @@ struct JpegTables {
     uint8_t first_block_of_comp[4];
 };
 
-__constant__ uint8_t kNatural[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
-                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
-                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
 struct JpegDev {
     const uint8_t* raw;
@@ -220,8 +217,6 @@ struct SmemTables {
     int maxcode[6][18];
     int valoff[6][18];
     uint8_t vals[6][256];
-    uint8_t comp_of_block[8];
-    uint8_t natural[64];
 };
 
 __device__ __forceinline__ uint32_t peek32(const uint32_t* __restrict__ words, uint32_t p) {
@@ -248,11 +243,6 @@ __device__ __forceinline__ void grid_barrier(int* counter, unsigned nblocks) {
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 
@@ -394,8 +384,6 @@ __global__ void __launch_bounds__(kDecodeThreads) jpeg_entropy_simple_kernel(Jpe
         // lut / maxcode / valoff / vals are the leading members of both structs, in the same order
         constexpr int kWords = (sizeof(T.lut) + sizeof(T.lut2) + sizeof(T.base16) + sizeof(T.maxcode) + sizeof(T.valoff) + sizeof(T.vals)) / 4;
         for (int i = threadIdx.x; i < kWords; i += kDecodeThreads) dst[i] = src[i];
-        if (threadIdx.x < 8) T.comp_of_block[threadIdx.x] = J.tables->comp_of_block[threadIdx.x];
-        if (threadIdx.x < 64) T.natural[threadIdx.x] = kNatural[threadIdx.x];
     }
     __syncthreads();
     const int i = blockIdx.x * kDecodeThreads + threadIdx.x;
@@ -511,8 +499,6 @@ __global__ void __launch_bounds__(kHypThreads) jpeg_entropy_kernel(JpegDev J) {
         uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
         constexpr int kWords = (sizeof(T.lut) + sizeof(T.lut2) + sizeof(T.base16) + sizeof(T.maxcode) + sizeof(T.valoff) + sizeof(T.vals)) / 4;
         for (int i = threadIdx.x; i < kWords; i += kHypThreads) dst[i] = src[i];
-        if (threadIdx.x < 8) T.comp_of_block[threadIdx.x] = J.tables->comp_of_block[threadIdx.x];
-        if (threadIdx.x < 64) T.natural[threadIdx.x] = kNatural[threadIdx.x];
     }
     __syncthreads();
     const int sub = threadIdx.x >> 3, lane = threadIdx.x & 7;
