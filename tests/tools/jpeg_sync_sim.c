@@ -1,7 +1,7 @@
 /* dev analysis: how far does a speculative decode (guess: block of component c starts at bit i*S) run before it merges
- * with the true parse?  gcc -O2 -o tools/jpeg_sync_sim tools/jpeg_sync_sim.c && ./jpeg_sync_sim file.jpg [S] */
+ * with the true parse?  gcc -O2 -o tests/tools/jpeg_sync_sim tests/tools/jpeg_sync_sim.c && ./jpeg_sync_sim file.jpg [S] */
 #include <stdio.h>
-#include "../oracle/jpeg_ref.c"
+#include "../../oracle/jpeg_ref.c"
 
 static uint8_t* U; static size_t NU;   /* unstuffed stream */
 static uint32_t peekU(size_t p) { uint64_t v = 0; size_t b = p >> 3; for (int k = 0; k < 8; ++k) v = (v << 8) | (b + k < NU ? U[b + k] : 0xFF); return (uint32_t)((v << (p & 7)) >> 32); }
@@ -26,22 +26,19 @@ int main(int argc, char** argv) {
     bpm = 0; for (int c = 0; c < j.ncomp; ++c) for (int k = 0; k < j.hs[c] * j.vs[c]; ++k) comp_of[bpm++] = c;
     size_t bits = NU * 8; uint16_t* truth = calloc(bits + 64, 2);   /* (z<<4|c)+1 at every true symbol start */
     St s = {0, 0, 0}; while (s.p + 8 <= bits) { truth[s.p] = (uint16_t)(((s.z << 4) | s.c) + 1); step(&s); }
-    size_t nsub = (bits + S - 1) / S;
-    int span = argc > 3 ? atoi(argv[3]) : 1;     /* subsequences each hypothesis decodes in round 0 */
-    St* tb = calloc(nsub + 2, sizeof(St)); { St t = {0,0,0}; for (size_t i = 0; i <= nsub; ++i) { while (t.p < i * S && t.p + 8 <= bits) step(&t); tb[i] = t; } }
-    long ok_plural = 0, wrong_plural = 0, none = 0, h0_ok = 0, any_ok = 0; 
-    char* good = calloc(nsub + 2, 1); good[0] = 1;
-    for (size_t i = 0; i + span < nsub; ++i) {
-        St e[8]; int cnt[8] = {0};
-        for (int h = 0; h < bpm; ++h) { St t = {i * S, 0, h}; while (t.p < (i + span) * S && t.p + 8 <= bits) step(&t); e[h] = t; }
-        int best = 0; for (int h = 0; h < bpm; ++h) { for (int g = 0; g < bpm; ++g) if (e[g].p == e[h].p && e[g].z == e[h].z && e[g].c == e[h].c) cnt[h]++; if (cnt[h] > cnt[best]) best = h; }
-        St T = tb[i + span]; int is_ok = e[best].p == T.p && e[best].z == T.z && e[best].c == T.c;
-        int anyok = 0; for (int h = 0; h < bpm; ++h) if (e[h].p == T.p && e[h].z == T.z && e[h].c == T.c) anyok = 1;
-        any_ok += anyok; h0_ok += (e[0].p == T.p && e[0].z == T.z && e[0].c == T.c);
-        if (cnt[best] >= 2) { if (is_ok) ok_plural++; else wrong_plural++; } else { none++; }
-        good[i + span] = is_ok;
+    size_t nsub = (bits + S - 1) / S; long hist[64] = {0}; size_t worst = 0, worst_i = 0; double sum = 0; long hist6[64] = {0}; size_t worst6 = 0; double sum6 = 0;
+    for (size_t i = 1; i < nsub; ++i) {
+        size_t best = (size_t)-1;
+        for (int h = 0; h < bpm; ++h) {
+            St t = {i * S, 0, h}; size_t lim = i * S + 4000 * S;
+            while (t.p + 8 <= bits && t.p < lim && truth[t.p] != (uint16_t)(((t.z << 4) | t.c) + 1)) step(&t);
+            size_t dist = (t.p - i * S) / S;
+            if (h == 0) { sum += dist; if (dist > worst) { worst = dist; worst_i = i; } hist[dist < 63 ? dist : 63]++; }
+            if (dist < best) best = dist;
+        }
+        sum6 += best; if (best > worst6) worst6 = best; hist6[best < 63 ? best : 63]++;
     }
-    size_t run = 0, worst = 0, bad = 0; for (size_t i = 0; i < nsub; ++i) { if (!good[i] && i >= (size_t)span) { run++; bad++; if (run > worst) worst = run; } else run = 0; }
-    printf("S=%zu span=%d nsub=%zu: plurality right %ld wrong %ld, no plurality %ld; h0 right %ld, any right %ld; bad boundaries %zu, longest bad run %zu\n", S, span, nsub, ok_plural, wrong_plural, none, h0_ok, any_ok, bad, worst);
+    printf("S=%zu nsub=%zu  c=0 guess: mean %.2f worst %zu (at sub %zu)   best-of-%d: mean %.2f worst %zu\n", S, nsub, sum / nsub, worst, worst_i, bpm, sum6 / nsub, worst6);
+    printf("hist c=0  :"); for (int k = 0; k < 64; ++k) if (hist[k]) printf(" %d:%ld", k, hist[k]); printf("\nhist best :"); for (int k = 0; k < 64; ++k) if (hist6[k]) printf(" %d:%ld", k, hist6[k]); printf("\n");
     return 0;
 }

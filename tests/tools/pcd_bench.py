@@ -8,7 +8,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import rm_radar_b200 as rr  # noqa: E402
 from oracle import locate_oracle as lo  # noqa: E402
 from tests import fixtures as fx  # noqa: E402

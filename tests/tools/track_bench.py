@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Tracker measurement (host code, no GPU needed): Tracker::update through the C ABI on the record
-array `rmr_run_once` fills, against the numpy oracle.  python tools/track_bench.py [robots] [frames]"""
+array `rmr_run_once` fills, against the numpy oracle.  python tests/tools/track_bench.py [robots] [frames]"""
 import ctypes as C
 import json
 import os
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import rm_radar_b200 as rr  # noqa: E402
 from oracle import track_oracle as to  # noqa: E402
