@@ -76,3 +76,23 @@ def unpack_records(gathered: torch.Tensor):
                                area=float(row[7])))
         out.append(robots)
     return out
+
+
+def robots_from_records(gathered: torch.Tensor) -> list:
+    """[world, max_cars, 8] -> one flat list of `Robot` (rank order, record order) for a field-level `Tracker`.
+
+    The exchanged record carries the winning label and its confidence, not the armour list, so a detected robot gets one
+    stand-in armour (label, confidence): `Robot::feature` (robot.cpp:102-122) of it is the one-hot vector the reference
+    would build from a single armour.  This is the consumer SURVEY §8f names for the tracker: "the all-gathered positions".
+    """
+    from . import Detection, Robot
+    robots = []
+    for per_rank in unpack_records(gathered):
+        for r in per_rank:
+            robot = Robot()
+            if r["label"] >= 0:
+                robot.label, robot.confidence = r["label"], r["confidence"]
+                robot.armors = [Detection(0.0, 0.0, 0.0, 0.0, float(r["label"]), r["confidence"])]
+            robot.location = r["location"]
+            robots.append(robot)
+    return robots

@@ -74,3 +74,40 @@ def test_pack_records_fast_path_matches_generic():
     fast = rdist.pack_records(recs, 6, MAX_CARS)
     slow = rdist.pack_records([recs[i] for i in range(6)], 6, MAX_CARS)
     assert torch.equal(fast, slow)
+
+
+def tracker_worker(rank, world, port):
+    """Two camera streams, each seeing its own moving robots; every rank tracks the union after the all-gather."""
+    import rm_radar_b200 as rr
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        tracker = rr.Tracker([0.2, 0.2, 0.2], 12, init_thresh=3)
+        t = 0
+        for frame in range(6):
+            t += 40_000_000
+            recs = [SimpleNamespace(label=3 * rank + i, is_detected=1, confidence=0.8, is_located=1,
+                                    location=(10.0 * rank + i + 0.02 * frame, 1.0 + i, 0.0), rect=(0.0, 0.0, 10.0, 10.0))
+                    for i in range(2 + rank)]
+            block = rdist.pack_records(recs, len(recs), MAX_CARS)
+            robots = rdist.robots_from_records(rdist.all_gather_records(block))
+            assert len(robots) == 2 + 3                      # rank 0 publishes 2 robots, rank 1 publishes 3
+            tracker.update(robots, t)
+        tracks = tracker.tracks()
+        assert len(tracks) == 5 and all(k["state"] == 1 for k in tracks)          # confirmed on every rank
+        assert sorted(k["label"] for k in tracks) == [0, 1, 3, 4, 5]
+        assert all(r.track_state == 1 for r in robots)
+        # every rank holds the same field-level picture
+        summary = torch.tensor([[k["id"], k["label"], *k["location"]] for k in tracks], dtype=torch.float32)
+        both = [torch.empty_like(summary) for _ in range(world)]
+        dist.all_gather(both, summary)
+        assert torch.allclose(both[0], both[1])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_field_level_tracker_over_gathered_records_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(tracker_worker, args=(2, port), nprocs=2, join=True)
