@@ -37,6 +37,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_JSON_FD = None
+
+
+def own_stdout():
+    """Keep stdout for the one JSON line: whatever libraries print there (NCCL's version banner) goes to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        while data:
+            data = data[os.write(_JSON_FD, data):]
+
+
 def make_inputs(seed):
     import cv2
     from tests import fixtures as fx
@@ -153,8 +175,8 @@ def run_reference(args, rank, world):
         return
     frame, bg, cloud, fx = make_inputs(1)
     if not fx.have_onnx():
-        print(json.dumps({"impl": "reference", "unavailable": "fp32 ONNX copies (rm_radar_b200/engines/*.onnx) are not in "
-                          "this snapshot; run __graft_entry__.build() where /root/reference is mounted"}), flush=True)
+        emit({"impl": "reference", "unavailable": "fp32 ONNX copies (rm_radar_b200/engines/*.onnx) are not in "
+              "this snapshot; run __graft_entry__.build() where /root/reference is mounted"})
         return
     r = cpu_path(frame, bg, cloud, fx, budget_s=120.0, max_frames=max(1, args.steps))
     line = {"impl": "reference", "metric": "detect+locate frames/sec", "value": r["value"], "unit": "frames/s",
@@ -163,7 +185,7 @@ def run_reference(args, rank, world):
             "dtype": "f32", "data": "synthetic", "config": config_dict(world),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(world):
@@ -386,7 +408,7 @@ def run_ours(args, rank, world, local_rank):
         except Exception as e:   # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {e}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -402,6 +424,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    own_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
