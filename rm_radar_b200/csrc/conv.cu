@@ -879,6 +879,10 @@ ConvLaunch make_conv_launch(const ConvDesc& d) {
     if (!conv_umma_supported(d)) throw CudaError("conv shape not supported by the tcgen05 path");
     ConvLaunch l;
     std::memset(&l, 0, sizeof(l));
+    if (conv2_enabled() && conv2_supported(d)) {
+        make_conv2_launch(d, l);
+        return l;
+    }
     ConvParams& p = l.p;
     p.n = d.n; p.h_out = d.h_out; p.w_out = d.w_out; p.cout = d.cout;
     p.bk = (d.cin % 64 == 0) ? 64 : 32;
@@ -1031,12 +1035,14 @@ static bool g_use_pdl = true;
 // scratch of a split-K launch: one arrival counter per output tile (zero between launches), then the
 // fp32 partial tiles [tile][split][128][part_ld]
 size_t conv_scratch_bytes(const ConvLaunch& l) {
+    if (l.v2) return conv2_scratch_bytes(l);
     if (l.p.splits <= 1) return 0;
     const size_t tiles = static_cast<size_t>(l.grid.x) * l.grid.y;
     return (tiles * sizeof(int) + 255) / 256 * 256 + tiles * l.p.splits * 128 * l.p.part_ld * sizeof(float);
 }
 
 void conv_bind_scratch(ConvLaunch& l, void* zeroed_base) {
+    if (l.v2) { conv2_bind_scratch(l, zeroed_base); return; }
     if (l.p.splits <= 1) return;
     const size_t tiles = static_cast<size_t>(l.grid.x) * l.grid.y;
     l.p.counters = static_cast<int*>(zeroed_base);
@@ -1045,8 +1051,12 @@ void conv_bind_scratch(ConvLaunch& l, void* zeroed_base) {
 
 
 void conv_init() {
-    static std::once_flag once;
-    std::call_once(once, [] {
+    conv2_init();
+    // function attributes are per device (primary context): one flag per device ordinal
+    static std::once_flag once_dev[64];
+    int dev = 0;
+    RMR_CUDA(cudaGetDevice(&dev));
+    std::call_once(once_dev[dev & 63], [] {
         auto prep = [](auto kernel, int smem) {
             RMR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             RMR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -1066,6 +1076,7 @@ void conv_init() {
 }
 
 void launch_conv_umma(const ConvLaunch& l, cudaStream_t s, bool pdl) {
+    if (l.v2) { launch_conv2(l, s, pdl); return; }
     conv_init();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = l.grid;

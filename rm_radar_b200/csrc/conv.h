@@ -52,9 +52,40 @@ struct ConvParams {
     long long* dbg;                   // optional per-CTA clock64 timeline (64 slots per CTA), tests only
 };
 
+// Round-2 kernel (conv2.cu): persistent CTAs, resident weights, halo patches, double-buffered TMEM.
+struct Conv2Params {
+    int n, h_out, w_out, cout;
+    int tw, th, tn, tiles_w, tiles_h, tiles_n, m_tiles;
+    int block_n, n_tiles, splits, ns_total;   // ns_total = n_tiles * splits: (channel slice, K split) pairs
+    int gm;                                   // CTAs per pair; a CTA takes pixel tiles j, j + gm, ...
+    int units_per_split;                      // split granularity: (tap, chunk) pairs, or channel chunks in halo mode
+    int bk, kpt, ntaps, cin, cin_coff;
+    int halo, pw;                             // halo mode: one [18][pw]-pixel patch per channel chunk
+    uint32_t row_bytes;                       // bk * 2
+    int4 tap[9];                              // (channel add, dw, h-parity, dh)
+    uint32_t a_stage, a_tx, b_stage, a_off, b_off;   // shared-memory geometry (bytes)
+    int sa, sb, b_resident;
+    uint32_t idesc, sbo_a, sbo_b, layout;
+    uint32_t acc_stride, tmem_cols;
+    void* out;
+    int out_pitch, out_coff, out_f32;
+    const float* bias;
+    int act;                                  // 0 none, 1 SiLU (tanh form), 2 SiLU (ex2 + rcp)
+    const __half* res;
+    int res_pitch, res_coff;
+    __half* dup;
+    int dup_pitch, dup_coff, dup_mode;
+    int vec_ok;
+    int part_ld;
+    float* partial;
+    int* counters;
+};
+
 struct ConvLaunch {
     CUtensorMap tm_a, tm_b;
     ConvParams p;
+    Conv2Params q;
+    int v2 = 0;          // 1: launch conv2_kernel with q; 0: the round-1 kernel with p
     dim3 grid;
     int smem_bytes = 0;
     double flops = 0;
@@ -67,6 +98,14 @@ ConvLaunch make_conv_launch(const ConvDesc& d);
 size_t conv_scratch_bytes(const ConvLaunch& l);
 void conv_bind_scratch(ConvLaunch& l, void* zeroed_base);
 void launch_conv_umma(const ConvLaunch& l, cudaStream_t s, bool pdl = true);
+// conv2.cu
+bool conv2_enabled();
+bool conv2_supported(const ConvDesc& d);
+void make_conv2_launch(const ConvDesc& d, ConvLaunch& l);
+size_t conv2_scratch_bytes(const ConvLaunch& l);
+void conv2_bind_scratch(ConvLaunch& l, void* zeroed_base);
+void conv2_init();
+void launch_conv2(const ConvLaunch& l, cudaStream_t s, bool pdl);
 // generic direct convolution on CUDA cores: the stem (Cin=3) and the on-device checker for tests
 void launch_conv_simt(const ConvDesc& d, cudaStream_t s);
 

@@ -1,0 +1,345 @@
+// Microbenchmark 4 (round 2): the hardware limits the conv main loop is designed against.
+//   1. tcgen05.mma rate with operands resident in shared memory (no TMA traffic), N = 32..256, cta_group 1 / 2
+//   2. steady-state TMA ingest per SM with a deep ring, all SMs streaming an L2-resident tensor
+//   3. the two together: ring of (A, B) stages, four MMAs per stage, A reloaded every `a_every` stages
+//      (1 = one box per filter tap, 9 = one halo patch per nine taps)
+//   4. SiLU through tanh.approx.f32 (one MUFU) against ex2 + rcp (two MUFU): error against double
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/umma_bench tools/umma_bench.cu
+#include "../rm_radar_b200/csrc/common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+using namespace rmr;
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
+
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ bool elect1() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ void fill_smem(uint8_t* base, int bytes) {
+    __half* h = reinterpret_cast<__half*>(base);
+    for (int i = threadIdx.x; i < bytes / 2; i += blockDim.x) h[i] = __float2half(0.03125f * static_cast<float>((i * 7 + (i >> 6)) % 13 - 6));
+}
+
+// ---------------------------------------------------------------- 1. MMA rate
+template <bool kPair>
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int groups, int depth, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar[16];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const int nb = kPair ? n / 2 : n;             // weight rows held by this CTA
+    const uint32_t a_bytes = 16384, b_bytes = nb * 128;
+    fill_smem(gen, 2 * (a_bytes + b_bytes));
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; ++i) mbar_init(smem_u32(&bar[i]), 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        if (kPair) { tmem_alloc_2sm(smem_u32(&tmem_slot), 512); tmem_relinquish_2sm(); }
+        else { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (kPair) cluster_sync_all();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>((kPair ? 256 : 128) >> 4) << 24);
+    if (warp == 1 && rank == 0) {
+        // warp-converged loop, one elected lane issues (issued from divergent code every UTCHMMA is wrapped in a lane loop)
+        const bool leader = elect1();
+        const uint64_t ad0 = umma_smem_desc(base, 1024u, 2u);
+        const uint64_t bd0 = umma_smem_desc(base + 2 * a_bytes, 1024u, 2u);
+        const long long t0 = clock64();
+        for (int g = 0; g < groups; ++g) {
+            const int slot = g % depth;
+            if (g >= depth) mbar_wait_fast(smem_u32(&bar[slot]), ((g / depth) - 1) & 1);
+            if (leader) {
+                const uint64_t ad = ad0 + static_cast<uint64_t>((g & 1) * (a_bytes >> 4));
+                const uint64_t bd = bd0 + static_cast<uint64_t>((g & 1) * (b_bytes >> 4));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (kPair) umma_f16_2sm(tmem, ad + 2u * k, bd + 2u * k, idesc, (g | k) != 0);
+                    else umma_f16(tmem, ad + 2u * k, bd + 2u * k, idesc, (g | k) != 0);
+                }
+                if (kPair) umma_commit_2sm(smem_u32(&bar[slot]), 1);
+                else umma_commit(smem_u32(&bar[slot]));
+            }
+            __syncwarp();
+        }
+        const long long t1 = clock64();
+        const int last = groups - 1;
+        mbar_wait_fast(smem_u32(&bar[last % depth]), (last / depth) & 1);
+        const long long t2 = clock64();
+        if (leader) {
+            out[blockIdx.x * 2] = t2 - t0;
+            out[blockIdx.x * 2 + 1] = t1 - t0;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (kPair) cluster_sync_all();
+    if (warp == 0) {
+        tc_fence_after();
+        if (kPair) tmem_dealloc_2sm(tmem, 512);
+        else tmem_dealloc(tmem, 512);
+    }
+}
+
+template <bool kPair>
+void run_mma_rate(int n, int grid, int depth) {
+    const int groups = 512;
+    long long* d; CK(cudaMalloc(&d, sizeof(long long) * 2 * grid));
+    CK(cudaMemset(d, 0, sizeof(long long) * 2 * grid));
+    const int smem = 2 * (16384 + n * 128) + 1024;
+    CK(cudaFuncSetAttribute(mma_rate_kernel<kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = kPair ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaError_t e = cudaLaunchKernelEx(&cfg, mma_rate_kernel<kPair>, n, groups, depth, d);
+        if (e != cudaSuccess) { printf("mma %s N %d grid %d: launch failed: %s\n", kPair ? "2cta" : "1cta", n, grid, cudaGetErrorString(e)); cudaGetLastError(); cudaFree(d); return; }
+    }
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> h(2 * grid); CK(cudaMemcpy(h.data(), d, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost));
+    std::vector<long long> tot;
+    for (int i = 0; i < grid; i += (kPair ? 2 : 1)) tot.push_back(h[2 * i]);
+    std::sort(tot.begin(), tot.end());
+    const double med = static_cast<double>(tot[tot.size() / 2]);
+    const double per = med / (groups * 4);
+    const double floor_c = n / 2.0;   // tensor cycles of one 128 x N x 16 (per SM) MMA
+    printf("mma %s N %3d depth %2d grid %3d: %7.1f clk/MMA (tensor floor %5.1f -> %4.0f%%), issue-only %6.1f clk/MMA\n",
+           kPair ? "2cta" : "1cta", n, depth, grid, per, floor_c, 100.0 * floor_c / per, static_cast<double>(h[1]) / (groups * 4));
+    fflush(stdout);
+    cudaFree(d);
+}
+
+// ---------------------------------------------------------------- 2 + 3. TMA ring (+ MMAs)
+struct RingArgs {
+    int n;            // MMA N (0 = no MMAs: pure ingest)
+    int stages;       // ring depth
+    int a_every;      // A box reloaded every a_every k-blocks
+    int kblocks;      // k-blocks per CTA
+    int a_rows;       // rows of the A tensor (coordinate range)
+    int b_rows;
+};
+
+__global__ void __launch_bounds__(128, 1) ring_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                                                      RingArgs r, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full[16], empty[16], afull[2], aempty[2], done;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t a_bytes = 16384, b_bytes = (r.n ? r.n : 64) * 128;
+    const bool shared_a = r.a_every > 1;           // A lives in two patch slots instead of the ring
+    const uint32_t stage_bytes = shared_a ? b_bytes : a_bytes + b_bytes;
+    const uint32_t ring0 = base + (shared_a ? 2 * a_bytes : 0);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&afull[i]), 1); mbar_init(smem_u32(&aempty[i]), 1); }
+        mbar_init(smem_u32(&done), 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
+    }
+    if (warp == 2) { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>((r.n ? r.n : 64) >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+    long long t0 = 0;
+    if (warp == 0) {
+        // producer: A then B of every stage
+        const bool leader = elect1();
+        t0 = clock64();
+        int arow = (blockIdx.x * 977) % (r.a_rows - 128), brow = (blockIdx.x * 131) % (r.b_rows - 256);
+        for (int kb = 0; kb < r.kblocks; ++kb) {
+            const int s = kb % r.stages;
+            if (kb >= r.stages) mbar_wait_fast(smem_u32(&empty[s]), ((kb / r.stages) - 1) & 1);
+            const uint32_t fb = smem_u32(&full[s]);
+            if (shared_a) {
+                if (kb % r.a_every == 0) {
+                    const int ai = kb / r.a_every, as = ai & 1;
+                    if (ai >= 2) mbar_wait_fast(smem_u32(&aempty[as]), ((ai >> 1) - 1) & 1);
+                    if (leader) {
+                        mbar_expect_tx(smem_u32(&afull[as]), a_bytes);
+                        tma_load_2d(base + as * a_bytes, &tm_a, smem_u32(&afull[as]), 0, arow);
+                    }
+                    arow += 128; if (arow > r.a_rows - 128) arow = 0;
+                }
+                if (leader) {
+                    mbar_expect_tx(fb, b_bytes);
+                    tma_load_2d(ring0 + s * stage_bytes, &tm_b, fb, 0, brow);
+                }
+            } else {
+                if (leader) {
+                    mbar_expect_tx(fb, a_bytes + b_bytes);
+                    tma_load_2d(ring0 + s * stage_bytes, &tm_a, fb, 0, arow);
+                    tma_load_2d(ring0 + s * stage_bytes + a_bytes, &tm_b, fb, 0, brow);
+                }
+                arow += 128; if (arow > r.a_rows - 128) arow = 0;
+            }
+            __syncwarp();
+            brow += 256; if (brow > r.b_rows - 256) brow = 0;
+        }
+    } else if (warp == 1) {
+        // consumer: four MMAs per stage, commit frees the stage
+        const bool leader = elect1();
+        const uint64_t sdesc = umma_smem_desc(0, 1024u, 2u);
+        for (int kb = 0; kb < r.kblocks; ++kb) {
+            const int s = kb % r.stages;
+            uint32_t a_addr;
+            if (shared_a) {
+                const int ai = kb / r.a_every, as = ai & 1;
+                if (kb % r.a_every == 0) mbar_wait_fast(smem_u32(&afull[as]), (ai >> 1) & 1);
+                a_addr = base + as * a_bytes;
+            } else a_addr = ring0 + s * stage_bytes;
+            const uint32_t b_addr = shared_a ? ring0 + s * stage_bytes : ring0 + s * stage_bytes + a_bytes;
+            mbar_wait_fast(smem_u32(&full[s]), (kb / r.stages) & 1);
+            tc_fence_after();
+            const bool a_done = shared_a && (kb % r.a_every == r.a_every - 1 || kb == r.kblocks - 1);
+            if (leader) {
+                if (r.n) {
+                    const uint64_t ad = sdesc | ((a_addr & 0x3FFFF) >> 4), bd = sdesc | ((b_addr & 0x3FFFF) >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem, ad + 2u * k, bd + 2u * k, idesc, (kb | k) != 0);
+                    umma_commit(smem_u32(&empty[s]));
+                    if (a_done) umma_commit(smem_u32(&aempty[(kb / r.a_every) & 1]));
+                } else {
+                    mbar_arrive(smem_u32(&empty[s]));
+                    if (a_done) mbar_arrive(smem_u32(&aempty[(kb / r.a_every) & 1]));
+                }
+            }
+            __syncwarp();
+        }
+        if (leader) { if (r.n) umma_commit(smem_u32(&done)); else mbar_arrive(smem_u32(&done)); }
+        __syncwarp();
+    }
+    if (warp == 0) {
+        mbar_wait_fast(smem_u32(&done), 0);
+        if (lane == 0) out[blockIdx.x] = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+void run_ring(EncodeFn enc, __half* abuf, __half* bbuf, int a_rows, int b_rows, int n, int stages, int a_every, int grid) {
+    CUtensorMap ta, tb; cuuint32_t es[2] = {1, 1};
+    const int nb = n ? n : 64;
+    { cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(a_rows)}; cuuint64_t str[1] = {128}; cuuint32_t box[2] = {64, 128};
+      if (enc(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, abuf, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("encode A failed\n"); return; } }
+    { cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(b_rows)}; cuuint64_t str[1] = {128}; cuuint32_t box[2] = {64, static_cast<cuuint32_t>(nb)};
+      if (enc(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, bbuf, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("encode B failed\n"); return; } }
+    RingArgs r{n, stages, a_every, 360, a_rows, b_rows};
+    const uint32_t b_bytes = nb * 128;
+    const int smem = (a_every > 1 ? 2 * 16384 + stages * b_bytes : stages * (16384 + b_bytes)) + 1024;
+    if (smem > 227 * 1024) { printf("ring N %d stages %d a_every %d: does not fit (%d B)\n", n, stages, a_every, smem); return; }
+    long long* d; CK(cudaMalloc(&d, sizeof(long long) * grid));
+    CK(cudaFuncSetAttribute(ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int rep = 0; rep < 2; ++rep) ring_kernel<<<grid, 128, smem>>>(ta, tb, r, d);
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> h(grid); CK(cudaMemcpy(h.data(), d, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
+    std::sort(h.begin(), h.end());
+    const double med = static_cast<double>(h[grid / 2]);
+    const double bytes = r.kblocks * static_cast<double>(b_bytes) + (r.kblocks + a_every - 1) / a_every * 16384.0;
+    const double per_kb = med / r.kblocks;
+    printf("ring N %3d stages %2d a_every %d grid %3d: %7.1f clk/k-block (median; max CTA %7.1f), ingest %6.1f B/clk/SM",
+           n, stages, a_every, grid, per_kb, static_cast<double>(h[grid - 1]) / r.kblocks, bytes / med);
+    if (n) printf(", tensor floor %d clk -> %4.0f%%", 2 * n, 100.0 * 2 * n / per_kb);
+    printf("\n");
+    cudaFree(d);
+}
+
+// ---------------------------------------------------------------- 4. SiLU variants
+__global__ void silu_kernel(const float* x, float* y_tanh, float* y_exp, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+    y_tanh[i] = fmaf(0.5f * v, t, 0.5f * v);
+    float e, rc;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * v));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + e));
+    y_exp[i] = v * rc;
+}
+
+void run_silu() {
+    const int n = 1 << 20;
+    std::vector<float> x(n);
+    for (int i = 0; i < n; ++i) x[i] = -24.f + 48.f * static_cast<float>(i) / n;
+    float *dx, *dt, *de;
+    CK(cudaMalloc(&dx, n * 4)); CK(cudaMalloc(&dt, n * 4)); CK(cudaMalloc(&de, n * 4));
+    CK(cudaMemcpy(dx, x.data(), n * 4, cudaMemcpyHostToDevice));
+    silu_kernel<<<n / 256, 256>>>(dx, dt, de, n);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> yt(n), ye(n);
+    CK(cudaMemcpy(yt.data(), dt, n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ye.data(), de, n * 4, cudaMemcpyDeviceToHost));
+    double mt = 0, me = 0, rt = 0, re = 0, xt = 0, xe = 0, ht = 0, he = 0;
+    for (int i = 0; i < n; ++i) {
+        const double v = x[i], ref = v / (1.0 + std::exp(-v));
+        const double et = std::fabs(yt[i] - ref), ee = std::fabs(ye[i] - ref);
+        if (et > mt) { mt = et; xt = v; }
+        if (ee > me) { me = ee; xe = v; }
+        // error in units of the fp16 spacing at the result (what survives the fp16 store)
+        const double ulp = std::ldexp(1.0, std::max(-24, static_cast<int>(std::floor(std::log2(std::max(std::fabs(ref), 1e-30)))) - 10));
+        ht = std::max(ht, et / ulp); he = std::max(he, ee / ulp);
+        if (std::fabs(ref) > 1e-3) { rt = std::max(rt, et / std::fabs(ref)); re = std::max(re, ee / std::fabs(ref)); }
+    }
+    printf("silu tanh.approx : max abs err %.3e at x = %.3f, max rel err (|y| > 1e-3) %.3e, max err in fp16 ulps of y %.2f\n", mt, xt, rt, ht);
+    printf("silu ex2 + rcp   : max abs err %.3e at x = %.3f, max rel err (|y| > 1e-3) %.3e, max err in fp16 ulps of y %.2f\n", me, xe, re, he);
+    cudaFree(dx); cudaFree(dt); cudaFree(de);
+}
+
+int main(int argc, char** argv) {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    EncodeFn enc = reinterpret_cast<EncodeFn>(fn);
+    run_silu();
+    for (int grid : {1, 148}) {
+        for (int n : {32, 64, 128, 256}) run_mma_rate<false>(n, grid, 8);
+        run_mma_rate<false>(64, grid, 2);
+        run_mma_rate<false>(256, grid, 2);
+        for (int n : {64, 128, 256}) run_mma_rate<true>(n, grid == 1 ? 2 : grid, 8);
+    }
+    const int a_rows = 1 << 17, b_rows = 1 << 16;   // 16 MB + 8 MB: L2 resident after the warm-up launch
+    __half *abuf, *bbuf;
+    CK(cudaMalloc(&abuf, static_cast<size_t>(a_rows) * 128)); CK(cudaMalloc(&bbuf, static_cast<size_t>(b_rows) * 128));
+    CK(cudaMemset(abuf, 0, static_cast<size_t>(a_rows) * 128)); CK(cudaMemset(bbuf, 0, static_cast<size_t>(b_rows) * 128));
+    for (int grid : {1, 148}) {
+        for (int st : {3, 4, 6, 8}) run_ring(enc, abuf, bbuf, a_rows, b_rows, 0, st, 1, grid);      // pure ingest, 24 KB stages
+        run_ring(enc, abuf, bbuf, a_rows, b_rows, 0, 12, 9, grid);                                   // pure ingest, 8 KB stages
+        for (int n : {64, 128, 256}) {
+            for (int st : {4, 8}) run_ring(enc, abuf, bbuf, a_rows, b_rows, n, st, 1, grid);          // per-tap boxes
+            for (int st : {4, 6, 12}) run_ring(enc, abuf, bbuf, a_rows, b_rows, n, st, 9, grid);      // halo-like
+        }
+    }
+    return 0;
+}
