@@ -232,6 +232,12 @@ int rmr_conv_selftest(int n, int h_in, int w_in, int cin, int cout, int k, int s
 int rmr_conv_timeline(int n, int h_in, int w_in, int cin, int cout, int k, int stride, long long* out,
                       int capacity_ctas, int* n_ctas);
 
+/* planning aid (tests/tools only, no GPU needed): the launch plan the tcgen05 conv would use for one layer.
+ * out[16] = version (1 = conv.cu, 2 = conv2.cu), block_n, splits, halo, m_tiles, ctas, tiles per CTA,
+ * k-blocks per tile and CTA, activation slots, weight slots, weights resident (0/1), shared memory bytes,
+ * tile w, tile h, tile n, bk */
+int rmr_conv_plan(int n, int h_in, int w_in, int cin, int cout, int k, int stride, int* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -739,4 +739,29 @@ int rmr_conv_timeline(int n, int h_in, int w_in, int cin, int cout, int k, int s
     });
 }
 
+int rmr_conv_plan(int n, int h_in, int w_in, int cin, int cout, int k, int stride, int* out) {
+    return guarded([&] {
+        const int pad = k / 2;
+        ConvDesc d;
+        d.n = n; d.h_in = h_in; d.w_in = w_in; d.cin = cin; d.cin_pad = cin; d.cout = cout; d.cout_pad = (cout + 15) / 16 * 16;
+        d.k = k; d.stride = stride; d.act = 1;
+        d.h_out = (h_in + 2 * pad - k) / stride + 1; d.w_out = (w_in + 2 * pad - k) / stride + 1;
+        d.in_pitch = cin; d.out_pitch = d.cout_pad;
+        if (!conv_umma_supported(d)) throw std::invalid_argument("conv shape not supported by the tcgen05 path");
+        for (int i = 0; i < 16; ++i) out[i] = 0;
+        if (conv2_enabled() && conv2_supported(d)) {
+            ConvLaunch l;
+            std::memset(&l, 0, sizeof(l));
+            plan_conv2(d, l);
+            const Conv2Params& q = l.q;
+            const int kb = q.units_per_split * (q.halo ? 9 : 1);
+            const int v[16] = {2, q.block_n, q.splits, q.halo, q.m_tiles, static_cast<int>(l.grid.x), (q.m_tiles + q.gm - 1) / q.gm, kb,
+                               q.sa, q.sb, q.b_resident, l.smem_bytes, q.tw, q.th, q.tn, q.bk};
+            for (int i = 0; i < 16; ++i) out[i] = v[i];
+        } else {
+            out[0] = 1;   // the round-1 planner encodes tensor maps while planning: needs a device
+        }
+    });
+}
+
 }  // extern "C"

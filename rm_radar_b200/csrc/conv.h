@@ -101,6 +101,7 @@ void launch_conv_umma(const ConvLaunch& l, cudaStream_t s, bool pdl = true);
 // conv2.cu
 bool conv2_enabled();
 bool conv2_supported(const ConvDesc& d);
+void plan_conv2(const ConvDesc& d, ConvLaunch& l);      // host-only planning (no CUDA calls)
 void make_conv2_launch(const ConvDesc& d, ConvLaunch& l);
 size_t conv2_scratch_bytes(const ConvLaunch& l);
 void conv2_bind_scratch(ConvLaunch& l, void* zeroed_base);

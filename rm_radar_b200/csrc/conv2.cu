@@ -34,7 +34,7 @@ namespace {
 constexpr int kThreads2 = 384;
 constexpr int kMaxA = 8;     // activation ring slots
 constexpr int kMaxB = 40;    // weight slots (resident mode: one per k-block of the CTA)
-constexpr int kSmemMax = 227 * 1024;
+constexpr int kSmemMax = 224 * 1024;   // dynamic; ~2 KB of static shared memory (barriers, bias) sit beside it
 constexpr bool kConv2Default = false;   // until the parity run on the B200 is green
 
 __device__ __forceinline__ void pdl_wait2() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -154,7 +154,9 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         // ------------------------------ activation producer ------------------------------
         const bool leader = elect_one2();
         pdl_wait2();   // activations are the previous layer's output
-        uint32_t ga = 0;
+        // ring bookkeeping without divisions: (slot, phase) counters; a fresh barrier passes a wait on parity 1
+        int slot = 0;
+        uint32_t phase = 0;
         for (int mt = j0; mt < p.m_tiles; mt += p.gm) {
             int t = mt;
             const int tile_w = t % p.tiles_w; t /= p.tiles_w;
@@ -162,21 +164,20 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             const int tile_n = t / p.tiles_h;
             const int ow0 = tile_w * p.tw, oh0 = tile_h * p.th, n0 = tile_n * p.tn;
             if (kHalo) {
-                for (int c = u0; c < u1; ++c, ++ga) {
-                    const uint32_t slot = ga % p.sa;
-                    if (ga >= static_cast<uint32_t>(p.sa)) mbar_wait_spin(smem_u32(&bar_aempty[slot]), ((ga / p.sa) - 1) & 1);
+                for (int c = u0; c < u1; ++c) {
+                    mbar_wait_spin(smem_u32(&bar_aempty[slot]), phase ^ 1u);
                     if (leader) {
                         const uint32_t full = smem_u32(&bar_afull[slot]);
                         mbar_expect_tx(full, p.a_tx);
                         tma_load_4d(a_ring + slot * p.a_stage, &tm_a, full, p.cin_coff + c * p.bk, ow0 - 1, oh0 - 1, n0);
                     }
                     __syncwarp();
+                    if (++slot == p.sa) { slot = 0; phase ^= 1u; }
                 }
             } else {
                 int tap = u0 / p.kpt, kc = u0 - tap * p.kpt;
-                for (int u = u0; u < u1; ++u, ++ga) {
-                    const uint32_t slot = ga % p.sa;
-                    if (ga >= static_cast<uint32_t>(p.sa)) mbar_wait_spin(smem_u32(&bar_aempty[slot]), ((ga / p.sa) - 1) & 1);
+                for (int u = u0; u < u1; ++u) {
+                    mbar_wait_spin(smem_u32(&bar_aempty[slot]), phase ^ 1u);
                     const int4 tp = s_tap[tap];
                     if (leader) {
                         const uint32_t full = smem_u32(&bar_afull[slot]);
@@ -186,6 +187,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     }
                     __syncwarp();
                     if (++kc == p.kpt) { kc = 0; ++tap; }
+                    if (++slot == p.sa) { slot = 0; phase ^= 1u; }
                 }
             }
         }
@@ -193,31 +195,32 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         // ------------------------------ weight producer ------------------------------
         // weights are constants: no grid dependency.  Resident mode loads the CTA's slice once.
         const bool leader = elect_one2();
-        uint32_t gb = 0;
+        int slot = 0;
+        uint32_t phase = 0;
         for (int mt = j0; mt < p.m_tiles; mt += p.gm) {
             if (p.b_resident && mt != j0) break;
             if (kHalo) {
                 for (int c = u0; c < u1; ++c)
-                    for (int tap = 0; tap < 9; ++tap, ++gb) {
-                        const uint32_t slot = gb % p.sb;
-                        if (gb >= static_cast<uint32_t>(p.sb)) mbar_wait_spin(smem_u32(&bar_bempty[slot]), ((gb / p.sb) - 1) & 1);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait_spin(smem_u32(&bar_bempty[slot]), phase ^ 1u);
                         if (leader) {
                             const uint32_t full = smem_u32(&bar_bfull[slot]);
                             mbar_expect_tx(full, p.b_stage);
                             tma_load_2d(b_ring + slot * p.b_stage, &tm_b, full, tap * p.cin + c * p.bk, ch0);
                         }
                         __syncwarp();
+                        if (++slot == p.sb) { slot = 0; phase ^= 1u; }
                     }
             } else {
-                for (int u = u0; u < u1; ++u, ++gb) {
-                    const uint32_t slot = gb % p.sb;
-                    if (gb >= static_cast<uint32_t>(p.sb)) mbar_wait_spin(smem_u32(&bar_bempty[slot]), ((gb / p.sb) - 1) & 1);
+                for (int u = u0; u < u1; ++u) {
+                    mbar_wait_spin(smem_u32(&bar_bempty[slot]), phase ^ 1u);
                     if (leader) {
                         const uint32_t full = smem_u32(&bar_bfull[slot]);
                         mbar_expect_tx(full, p.b_stage);
                         tma_load_2d(b_ring + slot * p.b_stage, &tm_b, full, u * p.bk, ch0);
                     }
                     __syncwarp();
+                    if (++slot == p.sb) { slot = 0; phase ^= 1u; }
                 }
             }
         }
@@ -227,24 +230,24 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         const uint64_t adesc0 = umma_smem_desc(0, p.sbo_a, p.layout);
         const uint64_t bdesc0 = umma_smem_desc(0, p.sbo_b, p.layout);
         const int ksteps = p.bk >> 4;
-        uint32_t ga = 0, gb = 0, it = 0;
+        uint32_t it = 0;
+        int aslot = 0, bslot = 0;
+        uint32_t aphase = 0, bphase = 0;
         for (int mt = j0; mt < p.m_tiles; mt += p.gm, ++it) {
             const uint32_t ab = it & 1u;
-            if (it >= 2) mbar_wait_spin(smem_u32(&bar_accempty[ab]), ((it >> 1) - 1) & 1);
+            mbar_wait_spin(smem_u32(&bar_accempty[ab]), ((it >> 1) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t acc = tmem_base + ab * p.acc_stride;
             uint32_t accumulate = 0;
             if (kHalo) {
-                int kbi = 0;
-                for (int c = u0; c < u1; ++c, ++ga) {
-                    const uint32_t aslot = ga % p.sa;
-                    mbar_wait_spin(smem_u32(&bar_afull[aslot]), (ga / p.sa) & 1);
+                if (p.b_resident) { bslot = 0; bphase = 0; }   // resident weights: slot = k-block index, loaded once
+                for (int c = u0; c < u1; ++c) {
+                    mbar_wait_spin(smem_u32(&bar_afull[aslot]), aphase);
                     const uint32_t a_addr = a_ring + aslot * p.a_stage;
                     int dy = 0, dx = 0;
 #pragma unroll 1
-                    for (int tap = 0; tap < 9; ++tap, ++gb, ++kbi) {
-                        const uint32_t bslot = p.b_resident ? static_cast<uint32_t>(kbi) : gb % p.sb;
-                        if (!p.b_resident || it == 0) mbar_wait_spin(smem_u32(&bar_bfull[bslot]), p.b_resident ? 0u : (gb / p.sb) & 1);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (!p.b_resident || it == 0) mbar_wait_spin(smem_u32(&bar_bfull[bslot]), bphase);
                         tc_fence_after();
                         if (leader) {
                             const uint64_t ad = adesc0 | (((a_addr + (dy * p.pw + dx) * p.row_bytes) & 0x3FFFF) >> 4);
@@ -262,16 +265,16 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                         __syncwarp();
                         accumulate = 1;
                         if (++dx == 3) { dx = 0; ++dy; }
+                        if (++bslot == p.sb) { bslot = 0; bphase ^= 1u; }
                     }
+                    if (++aslot == p.sa) { aslot = 0; aphase ^= 1u; }
                 }
             } else {
-                int kbi = 0;
+                if (p.b_resident) { bslot = 0; bphase = 0; }
 #pragma unroll 1
-                for (int u = u0; u < u1; ++u, ++ga, ++gb, ++kbi) {
-                    const uint32_t aslot = ga % p.sa;
-                    const uint32_t bslot = p.b_resident ? static_cast<uint32_t>(kbi) : gb % p.sb;
-                    if (!p.b_resident || it == 0) mbar_wait_spin(smem_u32(&bar_bfull[bslot]), p.b_resident ? 0u : (gb / p.sb) & 1);
-                    mbar_wait_spin(smem_u32(&bar_afull[aslot]), (ga / p.sa) & 1);
+                for (int u = u0; u < u1; ++u) {
+                    if (!p.b_resident || it == 0) mbar_wait_spin(smem_u32(&bar_bfull[bslot]), bphase);
+                    mbar_wait_spin(smem_u32(&bar_afull[aslot]), aphase);
                     tc_fence_after();
                     if (leader) {
                         const uint64_t ad = adesc0 | (((a_ring + aslot * p.a_stage) & 0x3FFFF) >> 4);
@@ -288,6 +291,8 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     }
                     __syncwarp();
                     accumulate = 1;
+                    if (++aslot == p.sa) { aslot = 0; aphase ^= 1u; }
+                    if (++bslot == p.sb) { bslot = 0; bphase ^= 1u; }
                 }
             }
             if (leader) umma_commit(smem_u32(&bar_accfull[ab]));   // accumulator of this tile complete
@@ -568,7 +573,9 @@ bool conv2_supported(const ConvDesc& d) {
     return true;
 }
 
-void make_conv2_launch(const ConvDesc& d, ConvLaunch& l) {
+// Host-only part: tile shape, channel tile, split-K, shared-memory layout (no CUDA calls: also used by the
+// plan dump of tools/conv_plan.py on a machine without a GPU).
+void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
     Conv2Params& p = l.q;
     std::memset(&p, 0, sizeof(p));
     l.v2 = 1;
@@ -615,28 +622,42 @@ void make_conv2_launch(const ConvDesc& d, ConvLaunch& l) {
         if (d.cout_pad % bn != 0) continue;
         if (force_n && bn != force_n && d.cout_pad % force_n == 0) continue;
         const int n_tiles = d.cout_pad / bn;
-        for (int splits = 1; splits <= 16; ++splits) {
-            if (force_splits && splits != force_splits) continue;
+        // split-K (deterministic: fp32 partial tiles through L2, last-arriving split reduces) stays available for
+        // experiments (RMR_CONV_SPLITS=n) but is not planned: a partial tile is 128 x N x 4 B written and read
+        // once per split — for the layers that would want it that is 10-30x the layer's own traffic (measured:
+        // 40x40x256 -> 384 stride 2 at batch 7, 8 splits: 228 us against 25 us for the round-1 kernel).  Narrower
+        // channel tiles give the small maps their parallelism instead: below N = 64 an MMA costs the same ~56
+        // issue cycles whatever N is, so more, narrower CTAs are free until the activation re-reads show.
+        const int max_splits = force_splits ? force_splits : 1;
+        for (int splits = 1; splits <= max_splits; ++splits) {
+            if (force_splits && splits != force_splits && units >= force_splits) continue;
             const int ups = (units + splits - 1) / splits;
             if ((units + ups - 1) / ups != splits) continue;       // no empty split
-            if (splits > 1 && ups * kb_per_unit < 4) continue;
             const long ns = static_cast<long>(n_tiles) * splits;
             const long gm = std::max<long>(1, std::min<long>(p.m_tiles, kSM / std::max<long>(1, std::min<long>(ns, kSM))));
             const long ctas = ns * gm;
             const double waves = std::ceil(static_cast<double>(ctas) / kSM);
+            const double busy = static_cast<double>(std::min<long>(ctas, kSM));
             const double tiles_per_cta = std::ceil(static_cast<double>(p.m_tiles) / gm);
             const int kb = ups * kb_per_unit;
-            // MMA slice: tensor cycles vs shared-memory port (A 128 rows + B bn rows, row_bytes/ksteps*... = 32 B per K=16)
-            const double a_write = p.halo ? 4096.0 / 9.0 * 1.6 : 4096.0;   // TMA bytes written per slice (halo: patch / 9 taps, 18x10 vs 128 px)
-            const bool resident = static_cast<double>(kb) * bn * p.bk * 2 <= 150.0 * 1024 && kb <= kMaxB;
-            const double b_write = (resident && tiles_per_cta > 1) ? bn * 32.0 / tiles_per_cta : bn * 32.0;
+            // one K = 16 slice (constants measured with tools/umma_bench.cu, profiles/r2_umma_bench.txt):
+            //   issue   ~56 clk per tcgen05.mma from one issuing thread (groups of 4 + wait + commit)
+            //   tensor  N / 2 clk
+            //   smem    (A 4096 B + B 32 N B read by the MMA + bytes TMA writes for the slice) / 128 B/clk
+            //   ingest  L2 -> SM: 125 B/clk for a lone SM, ~75 B/clk per SM when all 148 stream
+            const double a_write = p.halo ? 4096.0 * (18.0 * p.pw) / (9.0 * 128.0) : 4096.0;
+            const bool resident = static_cast<double>(kb) * bn * p.bk * 2 + (p.halo ? 2.0 : 4.0) * 16384 <= kSmemMax - 1024 && kb <= kMaxB;
+            const double b_write = resident ? bn * 32.0 / tiles_per_cta : bn * 32.0;
             const double smem_cyc = (4096.0 + bn * 32.0 + a_write + b_write) / 128.0;
-            const double mma = std::max(bn / 2.0, smem_cyc);
-            const double ingest = (a_write + b_write) / 48.0;     // L2 -> SM bytes per slice at ~48 B/clk/SM with all SMs busy
-            const double per_kb = ksteps * std::max(mma, ingest) + 40.0;
-            const double epi = 600.0 + bn * 6.0 + (splits > 1 ? 1500.0 : 0.0);
+            const double ingest_rate = std::min(125.0, 11000.0 / busy);
+            const double slice = std::max({56.0, bn / 2.0, smem_cyc, (a_write + b_write) / ingest_rate});
+            const double per_kb = ksteps * slice;
+            // epilogue of one tile: 8 warps, 32-column chunks (TMEM load, bias, SiLU, fp16 stores); overlaps the next
+            // tile's main loop, so a tile costs the larger of the two
+            const double epi = 500.0 + (bn > 64 ? (bn - 64) * 7.0 : 0.0) + (splits > 1 ? 4000.0 + bn * 30.0 * splits : 0.0);
             const double tile_cyc = std::max(kb * per_kb, epi);
-            const double cost = waves * (2600.0 + tiles_per_cta * tile_cyc + epi);
+            // per-CTA fixed cost: launch ramp, barrier init, TMEM allocation, first operands in flight, last epilogue
+            const double cost = waves * (2400.0 + tiles_per_cta * tile_cyc + epi);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_n = bn; best_splits = splits; }
         }
     }
@@ -710,6 +731,17 @@ void make_conv2_launch(const ConvDesc& d, ConvLaunch& l) {
     p.layout = (p.bk == 64) ? 2u : 4u;
     p.sbo_b = 8u * p.row_bytes;
     p.sbo_a = p.halo ? static_cast<uint32_t>(p.pw) * p.row_bytes : 8u * p.row_bytes;
+    l.grid = dim3(static_cast<unsigned>(p.ns_total) * p.gm, 1, 1);
+    l.flops = 2.0 * d.n * d.h_out * d.w_out * static_cast<double>(d.cout) * d.k * d.k * d.cin;
+    // mirror what the generic plan code reads from the r1 parameter block
+    l.p.splits = p.splits; l.p.block_n = p.block_n; l.p.part_ld = p.part_ld; l.p.vec_ok = p.vec_ok;
+    l.p.halo = p.halo; l.p.slim = 0; l.p.pair = 0;
+}
+
+void make_conv2_launch(const ConvDesc& d, ConvLaunch& l) {
+    plan_conv2(d, l);
+    Conv2Params& p = l.q;
+    const int S = d.stride;
     const CUtensorMapSwizzle swz = (p.bk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
 
     const cuuint64_t cp = static_cast<cuuint64_t>(d.in_pitch);
@@ -733,11 +765,6 @@ void make_conv2_launch(const ConvDesc& d, ConvLaunch& l) {
         cuuint32_t box[2] = {static_cast<cuuint32_t>(p.bk), static_cast<cuuint32_t>(p.block_n)};
         encode2(&l.tm_b, const_cast<__half*>(d.w), 2, dims, strides, box, swz);
     }
-    l.grid = dim3(static_cast<unsigned>(p.ns_total) * p.gm, 1, 1);
-    l.flops = 2.0 * d.n * d.h_out * d.w_out * static_cast<double>(d.cout) * d.k * d.k * d.cin;
-    // mirror what the generic plan code reads from the r1 parameter block
-    l.p.splits = p.splits; l.p.block_n = p.block_n; l.p.part_ld = p.part_ld; l.p.vec_ok = p.vec_ok;
-    l.p.halo = p.halo; l.p.slim = 0; l.p.pair = 0;
 }
 
 size_t conv2_scratch_bytes(const ConvLaunch& l) {

@@ -918,6 +918,9 @@ void build_table(const uint8_t* bits, const uint8_t* vals, bool dc, uint32_t* lu
     int code = 0, k = 0;
     for (int l = 1; l <= 16; ++l) {
         valoff[l] = k - code;
+        // Kraft bound BEFORE any table write: an over-subscribed length would index past the lookup table
+        // (libjpeg rejects such DHT segments, jdhuff.c "Bogus Huffman table definition")
+        if (code + bits[l] > (1 << l) || k + bits[l] > 256) bad("over-subscribed Huffman table");
         for (int i = 0; i < bits[l]; ++i, ++k, ++code) {
             if (l <= kLutBits) {
                 const int first = code << (kLutBits - l);

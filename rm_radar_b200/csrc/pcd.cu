@@ -223,6 +223,14 @@ PcdHeader pcd_parse_header(const void* file, size_t size) {
     if (sizes.size() != fields.size()) sizes.assign(fields.size(), 4);
     if (types.size() != fields.size()) types.assign(fields.size(), "F");
     if (counts.size() != fields.size()) counts.assign(fields.size(), 1);
+    // SIZE in {1, 2, 4, 8} and COUNT >= 1, as in the PCD v0.7 grammar: a negative SIZE would put a field offset
+    // before the record (device reads in front of the upload buffer), a zero record would divide by zero
+    for (size_t i = 0; i < fields.size(); ++i) {
+        if (sizes[i] != 1 && sizes[i] != 2 && sizes[i] != 4 && sizes[i] != 8)
+            throw std::invalid_argument("PCD: SIZE must be 1, 2, 4 or 8");
+        if (counts[i] < 1 || counts[i] > 65536) throw std::invalid_argument("PCD: COUNT must be at least 1");
+    }
+    if (h.n_points > (1L << 31)) throw std::invalid_argument("PCD: POINTS out of range");
     int column = 0, offset = 0;
     for (size_t i = 0; i < fields.size(); ++i) {
         const int which = fields[i] == "x" ? 0 : fields[i] == "y" ? 1 : fields[i] == "z" ? 2 : -1;
@@ -239,7 +247,9 @@ PcdHeader pcd_parse_header(const void* file, size_t size) {
     h.record_bytes = offset;
     for (int k = 0; k < 3; ++k)
         if (h.column[k] < 0) throw std::invalid_argument("PCD: FIELDS must contain x, y and z");
-    if (h.binary && h.body_offset + static_cast<size_t>(h.n_points) * h.record_bytes > size)
+    if (h.record_bytes <= 0) throw std::invalid_argument("PCD: empty record");
+    // by division: POINTS * record_bytes may not wrap
+    if (h.binary && static_cast<size_t>(h.n_points) > (size - h.body_offset) / static_cast<size_t>(h.record_bytes))
         throw std::invalid_argument("PCD: binary body is shorter than POINTS records");
     return h;
 }

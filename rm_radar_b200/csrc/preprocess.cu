@@ -127,7 +127,9 @@ LetterboxGeom make_letterbox_geom(int src_x, int src_y, int src_w, int src_h, in
     g.bw = std::min(g.pw + g.left + right, out_w);
     g.bh = std::min(g.ph + g.top + bottom, out_h);
     g.clean = (g.pw + g.left + right == out_w && g.ph + g.top + bottom == out_h) ? 1 : 0;
-    g.stride_w = g.pw + g.left + right;
+    // the staging buffer is out_w wide: a degenerate ROI whose resized extent rounds to 0 (pw clamped to 1 after
+    // left/right were derived from round(w/ratio) = 0) would otherwise give a stride of out_w + 1
+    g.stride_w = std::min(g.pw + g.left + right, out_w);
     return g;
 }
 

@@ -8,7 +8,7 @@ timeout 600 python tools/conv_check.py 7 20 > gpurun_out/r2_conv_check_v2.txt 2>
 tail -75 gpurun_out/r2_conv_check_v2.txt
 RMR_HALO=0 timeout 600 python tools/conv_check.py 7 20 > gpurun_out/r2_conv_check_v2_nohalo.txt 2>&1
 tail -4 gpurun_out/r2_conv_check_v2_nohalo.txt
-RMR_CONV_V1=1 timeout 600 python tools/conv_check.py 7 20 > gpurun_out/r2_conv_check_v1.txt 2>&1
+RMR_CONV_V2=0 timeout 600 python tools/conv_check.py 7 20 > gpurun_out/r2_conv_check_v1.txt 2>&1
 tail -3 gpurun_out/r2_conv_check_v1.txt
 timeout 900 python -m pytest tests/test_gpu_conv.py -x -q 2>&1 | tail -15 > gpurun_out/r2_test_conv.log
 cat gpurun_out/r2_test_conv.log

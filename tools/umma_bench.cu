@@ -243,6 +243,126 @@ __global__ void __launch_bounds__(128, 1) ring_kernel(const __grid_constant__ CU
     if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+
+// ---------------------------------------------------------------- 1b. several issuing warps, one accumulator each
+__global__ void __launch_bounds__(256, 1) mma_multi_kernel(int n, int groups, int issuers, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar[4][8];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5;
+    const uint32_t a_bytes = 16384, b_bytes = n * 128;
+    fill_smem(gen, 2 * (a_bytes + b_bytes));
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < 4; ++w) for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bar[w][i]), 1);
+        fence_barrier_init();
+    }
+    if (warp == 7) { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+    if (warp < issuers) {
+        const bool leader = elect1();
+        const uint64_t ad0 = umma_smem_desc(base, 1024u, 2u);
+        const uint64_t bd0 = umma_smem_desc(base + 2 * a_bytes, 1024u, 2u);
+        const uint32_t acc = tmem + warp * 128;
+        int slot = 0; uint32_t phase = 0;
+        const long long t0 = clock64();
+        for (int g = 0; g < groups; ++g) {
+            mbar_wait_fast(smem_u32(&bar[warp][slot]), phase ^ 1u);   // fresh barrier: passes
+            if (leader) {
+                const uint64_t ad = ad0 + static_cast<uint64_t>((g & 1) * (a_bytes >> 4));
+                const uint64_t bd = bd0 + static_cast<uint64_t>((g & 1) * (b_bytes >> 4));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(acc, ad + 2u * k, bd + 2u * k, idesc, (g | k) != 0);
+                umma_commit(smem_u32(&bar[warp][slot]));
+            }
+            __syncwarp();
+            if (++slot == 8) { slot = 0; phase ^= 1u; }
+        }
+        // last commit of this warp
+        const int ls = (groups - 1) & 7;
+        mbar_wait_fast(smem_u32(&bar[warp][ls]), ((groups - 1) >> 3) & 1);
+        const long long t2 = clock64();
+        if (leader) out[blockIdx.x * 4 + warp] = t2 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 7) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+void run_mma_multi(int n, int issuers, int grid) {
+    const int groups = 512;
+    long long* d; CK(cudaMalloc(&d, sizeof(long long) * 4 * grid));
+    CK(cudaMemset(d, 0, sizeof(long long) * 4 * grid));
+    const int smem = 2 * (16384 + n * 128) + 1024;
+    CK(cudaFuncSetAttribute(mma_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int rep = 0; rep < 2; ++rep) mma_multi_kernel<<<grid, 256, smem>>>(n, groups, issuers, d);
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> h(4 * grid); CK(cudaMemcpy(h.data(), d, sizeof(long long) * 4 * grid, cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (int w = 0; w < issuers; ++w) mx = std::max(mx, h[(grid / 2) * 4 + w]);
+    const double per = static_cast<double>(mx) / (groups * 4 * issuers);
+    printf("mma 1cta N %3d issuers %d grid %3d: %7.1f clk per MMA per SM (tensor floor %5.1f -> %4.0f%%)\n", n, issuers, grid, per, n / 2.0,
+           100.0 * (n / 2.0) / per);
+    fflush(stdout);
+    cudaFree(d);
+}
+
+// ---------------------------------------------------------------- 2b. lean TMA ingest: producers = warps, no divisions in the loop
+struct IngestArgs { int stages, loads, rows_per_box, a_rows, producers; };
+__global__ void __launch_bounds__(192, 1) ingest_kernel(const __grid_constant__ CUtensorMap tm, IngestArgs r, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full[4][8], empty[4][8];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bytes = r.rows_per_box * 128;
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < 4; ++w) for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&full[w][i]), 1); mbar_init(smem_u32(&empty[w][i]), 1); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tm);
+    }
+    __syncthreads();
+    // warp w < producers: producer of ring w; warp 4: consumer of all rings (round robin)
+    if (warp < r.producers) {
+        const bool leader = elect1();
+        const uint32_t ring = base + warp * r.stages * bytes;
+        int slot = 0; uint32_t phase = 0;
+        int row = ((blockIdx.x * 4 + warp) * 1931) % (r.a_rows - 256);
+        const long long t0 = clock64();
+        for (int i = 0; i < r.loads; ++i) {
+            mbar_wait_fast(smem_u32(&empty[warp][slot]), phase ^ 1u);
+            if (leader) {
+                const uint32_t fb = smem_u32(&full[warp][slot]);
+                mbar_expect_tx(fb, bytes);
+                tma_load_2d(ring + slot * bytes, &tm, fb, 0, row);
+            }
+            __syncwarp();
+            row += r.rows_per_box; if (row > r.a_rows - 256) row = 0;
+            if (++slot == r.stages) { slot = 0; phase ^= 1u; }
+        }
+        // all loads of this ring consumed
+        const int ls = (r.loads - 1) % r.stages;
+        mbar_wait_fast(smem_u32(&empty[warp][ls]), ((r.loads - 1) / r.stages) & 1);
+        if (lane == 0) out[blockIdx.x * 4 + warp] = clock64() - t0;
+    } else if (warp == 4) {
+        const bool leader = elect1();
+        int slot = 0; uint32_t phase = 0;
+        for (int i = 0; i < r.loads; ++i) {
+            for (int w = 0; w < r.producers; ++w) {
+                mbar_wait_fast(smem_u32(&full[w][slot]), phase);
+                if (leader) mbar_arrive(smem_u32(&empty[w][slot]));
+                __syncwarp();
+            }
+            if (++slot == r.stages) { slot = 0; phase ^= 1u; }
+        }
+    }
+}
+
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -318,28 +438,54 @@ void run_silu() {
     cudaFree(dx); cudaFree(dt); cudaFree(de);
 }
 
+
+void run_ingest(EncodeFn enc, __half* abuf, int a_rows, int rows_per_box, int stages, int producers, int grid) {
+    CUtensorMap ta; cuuint32_t es[2] = {1, 1};
+    cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(a_rows)}; cuuint64_t str[1] = {128}; cuuint32_t box[2] = {64, static_cast<cuuint32_t>(rows_per_box)};
+    if (enc(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, abuf, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("encode failed\n"); return; }
+    IngestArgs r{stages, 512, rows_per_box, a_rows, producers};
+    const int bytes = rows_per_box * 128;
+    const int smem = producers * stages * bytes + 1024;
+    if (smem > 224 * 1024) { printf("ingest box %d B stages %d producers %d: does not fit\n", bytes, stages, producers); return; }
+    long long* d; CK(cudaMalloc(&d, sizeof(long long) * 4 * grid));
+    CK(cudaFuncSetAttribute(ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int rep = 0; rep < 2; ++rep) ingest_kernel<<<grid, 192, smem>>>(ta, r, d);
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> h(4 * grid); CK(cudaMemcpy(h.data(), d, sizeof(long long) * 4 * grid, cudaMemcpyDeviceToHost));
+    std::vector<long long> t;
+    for (int b = 0; b < grid; ++b) { long long mx = 0; for (int w = 0; w < producers; ++w) mx = std::max(mx, h[b * 4 + w]); t.push_back(mx); }
+    std::sort(t.begin(), t.end());
+    const double med = static_cast<double>(t[grid / 2]);
+    printf("ingest box %5d B stages %d producers %d grid %3d: %6.1f clk per load per producer, %6.1f B/clk/SM (slowest CTA %6.1f)\n", bytes, stages, producers,
+           grid, med / r.loads, static_cast<double>(producers) * r.loads * bytes / med, static_cast<double>(producers) * r.loads * bytes / t[grid - 1]);
+    fflush(stdout);
+    cudaFree(d);
+}
+
 int main(int argc, char** argv) {
     void* fn = nullptr; cudaDriverEntryPointQueryResult q;
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
     EncodeFn enc = reinterpret_cast<EncodeFn>(fn);
-    run_silu();
+    const bool quick = argc > 1;
+    if (!quick) run_silu();
     for (int grid : {1, 148}) {
         for (int n : {32, 64, 128, 256}) run_mma_rate<false>(n, grid, 8);
-        run_mma_rate<false>(64, grid, 2);
-        run_mma_rate<false>(256, grid, 2);
         for (int n : {64, 128, 256}) run_mma_rate<true>(n, grid == 1 ? 2 : grid, 8);
+        for (int n : {32, 64, 128})
+            for (int iss : {1, 2, 4}) run_mma_multi(n, iss, grid);
     }
     const int a_rows = 1 << 17, b_rows = 1 << 16;   // 16 MB + 8 MB: L2 resident after the warm-up launch
     __half *abuf, *bbuf;
     CK(cudaMalloc(&abuf, static_cast<size_t>(a_rows) * 128)); CK(cudaMalloc(&bbuf, static_cast<size_t>(b_rows) * 128));
     CK(cudaMemset(abuf, 0, static_cast<size_t>(a_rows) * 128)); CK(cudaMemset(bbuf, 0, static_cast<size_t>(b_rows) * 128));
     for (int grid : {1, 148}) {
-        for (int st : {3, 4, 6, 8}) run_ring(enc, abuf, bbuf, a_rows, b_rows, 0, st, 1, grid);      // pure ingest, 24 KB stages
-        run_ring(enc, abuf, bbuf, a_rows, b_rows, 0, 12, 9, grid);                                   // pure ingest, 8 KB stages
-        for (int n : {64, 128, 256}) {
-            for (int st : {4, 8}) run_ring(enc, abuf, bbuf, a_rows, b_rows, n, st, 1, grid);          // per-tap boxes
-            for (int st : {4, 6, 12}) run_ring(enc, abuf, bbuf, a_rows, b_rows, n, st, 9, grid);      // halo-like
-        }
+        for (int rows : {64, 128, 256})
+            for (int prod : {1, 2, 4})
+                run_ingest(enc, abuf, a_rows, rows, rows == 256 ? 1 + 4 / prod : 6 / prod + 2, prod, grid);
+        run_ingest(enc, abuf, a_rows, 128, 3, 4, grid);
+        run_ingest(enc, abuf, a_rows, 128, 3, 1, grid);
     }
+    (void)b_rows; (void)bbuf;
     return 0;
 }
