@@ -722,6 +722,7 @@ int rmr_conv_timeline(int n, int h_in, int w_in, int cin, int cout, int k, int s
             conv_bind_scratch(l, d_scratch);
         }
         const int ctas = static_cast<int>(l.grid.x * l.grid.y * l.grid.z);
+        if (l.v2) *n_ctas = -ctas;   // sign tells the caller which slot map applies (conv2.cu)
         long long* d_dbg;
         RMR_CUDA(cudaMalloc(&d_dbg, sizeof(long long) * 64 * ctas));
         RMR_CUDA(cudaMemset(d_dbg, 0, sizeof(long long) * 64 * ctas));
@@ -729,10 +730,12 @@ int rmr_conv_timeline(int n, int h_in, int w_in, int cin, int cout, int k, int s
         RMR_CUDA(cudaStreamCreate(&s));
         for (int i = 0; i < 3; ++i) launch_conv_umma(l, s);
         l.p.dbg = d_dbg;
+        l.q.dbg = d_dbg;
+        if (const char* f = std::getenv("RMR_DBG_MODE")) l.q.dbg_mode = std::atoi(f);
         if (const char* f = std::getenv("RMR_DBG_FLAGS")) l.p.dbg_flags = std::atoi(f);
         launch_conv_umma(l, s);
         RMR_CUDA(cudaStreamSynchronize(s));
-        *n_ctas = ctas;
+        *n_ctas = l.v2 ? -ctas : ctas;
         RMR_CUDA(cudaMemcpy(out, d_dbg, sizeof(long long) * 64 * std::min(ctas, capacity_ctas), cudaMemcpyDeviceToHost));
         cudaStreamDestroy(s);
         cudaFree(d_in); cudaFree(d_w); cudaFree(d_out); cudaFree(d_bias); cudaFree(d_dbg); cudaFree(d_scratch);
@@ -756,7 +759,7 @@ int rmr_conv_plan(int n, int h_in, int w_in, int cin, int cout, int k, int strid
             const Conv2Params& q = l.q;
             const int kb = q.units_per_split * (q.halo ? 9 : 1);
             const int v[16] = {2, q.block_n, q.splits, q.halo, q.m_tiles, static_cast<int>(l.grid.x), (q.m_tiles + q.gm - 1) / q.gm, kb,
-                               q.sa, q.sb, q.b_resident, l.smem_bytes, q.tw, q.th, q.tn, q.bk};
+                               q.sa, q.halo ? q.sb : q.g, q.b_resident, l.smem_bytes, q.tw, q.th, q.tn, q.bk};
             for (int i = 0; i < 16; ++i) out[i] = v[i];
         } else {
             out[0] = 1;   // the round-1 planner encodes tensor maps while planning: needs a device

@@ -63,8 +63,10 @@ struct Conv2Params {
     int halo, pw;                             // halo mode: one [18][pw]-pixel patch per channel chunk
     uint32_t row_bytes;                       // bk * 2
     int4 tap[9];                              // (channel add, dw, h-parity, dh)
-    uint32_t a_stage, a_tx, b_stage, a_off, b_off;   // shared-memory geometry (bytes)
-    int sa, sb, b_resident;
+    uint32_t a_stage, a_tx, b_stage, a_off, b_off;   // shared-memory geometry (bytes): stage strides, ring offsets
+    uint32_t a_kb, b_kb, b_in_stage;                 // bytes of one k-block of A / B; joint ring: offset of the weights inside a stage
+    int sa, sb, b_resident;                          // A (or joint) stages; B stages (halo streaming: three taps each)
+    int g, joint;                                    // per-tap mode: k-blocks per stage; weights travel in the A stage
     uint32_t idesc, sbo_a, sbo_b, layout;
     uint32_t acc_stride, tmem_cols;
     void* out;
@@ -79,10 +81,17 @@ struct Conv2Params {
     int part_ld;
     float* partial;
     int* counters;
+    long long* dbg;                           // optional per-CTA clock64 timeline (64 slots per CTA), tests only
+    int dbg_mode;                             // 0: per-tile phases; 1: per-k-block stamps of the first tile (A issue 4.., B issue 24.., consumed 44..)
+    // epilogue through shared memory + TMA (one [128 rows][32 channels] sub-tile per 32-column chunk)
+    int tma_epi, nchunks, esize_out;
+    uint32_t stage_off, sub_bytes, chunk_bytes;
 };
 
 struct ConvLaunch {
     CUtensorMap tm_a, tm_b;
+    CUtensorMap tm_out, tm_res;           // conv2 TMA epilogue: output tile store, shortcut tile load
+    CUtensorMap tm_dup[4];                // second destination: [0] plain copy, or the four (dy, dx) phases of the 2x upsample
     ConvParams p;
     Conv2Params q;
     int v2 = 0;          // 1: launch conv2_kernel with q; 0: the round-1 kernel with p

@@ -35,7 +35,7 @@ constexpr int kThreads2 = 384;
 constexpr int kMaxA = 8;     // activation ring slots
 constexpr int kMaxB = 40;    // weight slots (resident mode: one per k-block of the CTA)
 constexpr int kSmemMax = 224 * 1024;   // dynamic; ~2 KB of static shared memory (barriers, bias) sit beside it
-constexpr bool kConv2Default = false;   // until the parity run on the B200 is green
+constexpr bool kConv2Default = true;    // RMR_CONV_V2=0 falls back to the round-1 kernel (conv.cu)
 
 __device__ __forceinline__ void pdl_wait2() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch2() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -80,56 +80,78 @@ __device__ __forceinline__ float rcp_approx2(float x) {
     return y;
 }
 
+struct DupMaps {
+    CUtensorMap m[4];
+};
+
 // kHalo: 3x3 stride-1 layers, one [18][pw] pixel patch per channel chunk serves the nine taps.
 template <bool kHalo, bool kRes>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-             const __grid_constant__ Conv2Params p) {
+             const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
+             const __grid_constant__ DupMaps tm_dup, const __grid_constant__ Conv2Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_afull[kMaxA], bar_aempty[kMaxA];
     __shared__ __align__(8) uint64_t bar_bfull[kMaxB], bar_bempty[kMaxB];
-    __shared__ __align__(8) uint64_t bar_accfull[2], bar_accempty[2];
+    __shared__ __align__(8) uint64_t bar_accfull[2], bar_accempty[2], bar_bres;
+    // TMA epilogue, one set per 32-column sub-tile of the staging buffer: written by the epilogue (outready),
+    // read out by the TMA store (stfree), shortcut tile landed (resfull)
+    __shared__ __align__(8) uint64_t bar_outready[8], bar_stfree[8], bar_resfull[8];
     __shared__ uint32_t tmem_base_slot;
     __shared__ int4 s_tap[9];
     __shared__ float s_bias[256];
-    __shared__ int s_last;
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // profiling aid: slot 0 start, 1 setup done, 2 + 8 t + {0: A producer past its empty wait, 1: issuer past the
+    // accumulator wait, 2: first operands seen, 3: all MMAs of the tile issued, 4: epilogue sees the accumulator,
+    // 5: accumulator read out, 6: first epilogue group stored, 7: second group stored} for tiles t < 7, 60 exit
+    long long* dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 64 : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
-    // this CTA's slice: output channels [ch0, ch0 + block_n), k-blocks of split `split`, pixel tiles j, j + gm, ...
-    const int ns = blockIdx.x % p.ns_total;
-    const int j0 = blockIdx.x / p.ns_total;
-    const int nt = ns / p.splits;
-    const int split = ns - nt * p.splits;
+    // this CTA's slice: output channels [ch0, ch0 + block_n), pixel tiles j0, j0 + gm, ...
+    const int nt = blockIdx.x % p.n_tiles;
+    const int j0 = blockIdx.x / p.n_tiles;
     const int ch0 = nt * p.block_n;
-    // k-block range of this split: per-tap mode counts (tap, chunk) pairs tap-major, halo mode counts chunks
-    const int u0 = split * p.units_per_split;
-    const int u1 = min(u0 + p.units_per_split, kHalo ? p.kpt : p.ntaps * p.kpt);
+    // the K loop in units: per-tap mode counts (tap, chunk) pairs tap-major (= k-blocks in weight order), halo mode
+    // counts channel chunks (nine k-blocks each)
+    const int u0 = 0;
+    const int u1 = kHalo ? p.kpt : p.ntaps * p.kpt;
 
     if (warp == 1) {
         if (lane == 0) {
             tma_prefetch_desc(&tm_a);
             tma_prefetch_desc(&tm_b);
+            if (p.tma_epi) {
+                tma_prefetch_desc(&tm_out);
+                if (kRes && p.res != nullptr) tma_prefetch_desc(&tm_res);
+                if (p.dup_mode) tma_prefetch_desc(&tm_dup.m[0]);
+            }
         }
         if (lane < p.ntaps) s_tap[lane] = p.tap[lane];
     } else if (warp == 2) {
-        if (lane == 0) {
-            for (int i = 0; i < p.sa; ++i) {
-                mbar_init(smem_u32(&bar_afull[i]), 1);
-                mbar_init(smem_u32(&bar_aempty[i]), 1);
-            }
-            for (int i = 0; i < p.sb; ++i) {
-                mbar_init(smem_u32(&bar_bfull[i]), 1);
-                mbar_init(smem_u32(&bar_bempty[i]), 1);
-            }
-            for (int i = 0; i < 2; ++i) {
-                mbar_init(smem_u32(&bar_accfull[i]), 1);
-                mbar_init(smem_u32(&bar_accempty[i]), 8);   // one arrival per epilogue warp
-            }
-            fence_barrier_init();
+        // barrier init spread over the lanes (up to ~100 barriers: one thread would spend ~1500 cycles on them)
+        for (int i = lane; i < p.sa; i += 32) {
+            mbar_init(smem_u32(&bar_afull[i]), 1);
+            mbar_init(smem_u32(&bar_aempty[i]), 1);
         }
+        for (int i = lane; i < p.sb; i += 32) {
+            mbar_init(smem_u32(&bar_bfull[i]), 1);
+            mbar_init(smem_u32(&bar_bempty[i]), 1);
+        }
+        if (lane < 2) {
+            mbar_init(smem_u32(&bar_accfull[lane]), 1);
+            mbar_init(smem_u32(&bar_accempty[lane]), 8);   // one arrival per epilogue warp
+        }
+        if (lane == 2) mbar_init(smem_u32(&bar_bres), 1);
+        if (p.tma_epi && lane >= 8 && lane < 8 + p.nchunks) {
+            const int i = lane - 8;
+            mbar_init(smem_u32(&bar_outready[i]), 128);   // the four warps (one per TMEM lane quarter) of a chunk
+            mbar_init(smem_u32(&bar_stfree[i]), 1);
+            mbar_init(smem_u32(&bar_resfull[i]), 1);
+        }
+        fence_barrier_init();
         __syncwarp();
         tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
         tmem_relinquish();
@@ -142,6 +164,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
     pdl_launch2();
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
     const uint32_t a_ring = smem_base + p.a_off;
     const uint32_t b_ring = smem_base + p.b_off;
@@ -150,152 +173,321 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     // elected lane issues.  Issued from divergent code, ptxas wraps every UTMALDG / UTCHMMA / UTCBAR in an
     // ELECT + BRA.U.ANY lane loop (~150 cycles per instruction, tools/umma_bench.cu); with elect.sync under
     // warp-uniform control flow the bookkeeping stays in the uniform datapath and the MMAs issue back to back.
-    if (warp == 0) {
-        // ------------------------------ activation producer ------------------------------
+    // Stage granularity.  Every barrier round trip of the issuer (try_wait on a completed barrier ~150 cycles,
+    // commit, loop) costs about as much as four N <= 64 MMAs (profiles/r2_timeline3.txt: 300 cycles for two waits
+    // + 390 for four MMAs and a commit per k-block), so a stage carries several k-blocks:
+    //   per-tap mode   g k-blocks of activations per stage (+ their weights when the weights stream: "joint" ring)
+    //   halo mode      one patch = nine k-blocks; streamed weights come three taps per stage
+    //   resident weights  the whole slice on ONE barrier, waited for once
+    if (warp == 0 || warp == 1) {
+        // ------------------------------ operand producers ------------------------------
+        // warp 0: activations; warp 1: weights, and in per-tap mode every second activation box of a stage (one
+        // UTMALDG keeps the issuing warp busy for ~340 cycles, profiles/r2_timeline3.txt: a k-block of N <= 128 MMAs
+        // is shorter than that, so one warp cannot keep up).
+        // Weights come through a 3-D view (bk, Cout, k-block): ONE instruction loads the CTA's whole resident slice,
+        // or the g k-blocks of a joint stage, laid out k-block-major = one UMMA B tile after the other.
+        // (slot, phase) ring bookkeeping without divisions; a fresh barrier passes a wait on parity 1.
         const bool leader = elect_one2();
-        pdl_wait2();   // activations are the previous layer's output
-        // ring bookkeeping without divisions: (slot, phase) counters; a fresh barrier passes a wait on parity 1
-        int slot = 0;
-        uint32_t phase = 0;
-        for (int mt = j0; mt < p.m_tiles; mt += p.gm) {
-            int t = mt;
-            const int tile_w = t % p.tiles_w; t /= p.tiles_w;
-            const int tile_h = t % p.tiles_h;
-            const int tile_n = t / p.tiles_h;
-            const int ow0 = tile_w * p.tw, oh0 = tile_h * p.th, n0 = tile_n * p.tn;
-            if (kHalo) {
-                for (int c = u0; c < u1; ++c) {
-                    mbar_wait_spin(smem_u32(&bar_aempty[slot]), phase ^ 1u);
-                    if (leader) {
-                        const uint32_t full = smem_u32(&bar_afull[slot]);
-                        mbar_expect_tx(full, p.a_tx);
-                        tma_load_4d(a_ring + slot * p.a_stage, &tm_a, full, p.cin_coff + c * p.bk, ow0 - 1, oh0 - 1, n0);
-                    }
-                    __syncwarp();
-                    if (++slot == p.sa) { slot = 0; phase ^= 1u; }
-                }
-            } else {
-                int tap = u0 / p.kpt, kc = u0 - tap * p.kpt;
-                for (int u = u0; u < u1; ++u) {
-                    mbar_wait_spin(smem_u32(&bar_aempty[slot]), phase ^ 1u);
-                    const int4 tp = s_tap[tap];
-                    if (leader) {
-                        const uint32_t full = smem_u32(&bar_afull[slot]);
-                        mbar_expect_tx(full, p.a_tx);
-                        tma_load_5d(a_ring + slot * p.a_stage, &tm_a, full, p.cin_coff + tp.x + kc * p.bk, ow0 + tp.y, tp.z,
-                                    oh0 + tp.w, n0);
-                    }
-                    __syncwarp();
-                    if (++kc == p.kpt) { kc = 0; ++tap; }
-                    if (++slot == p.sa) { slot = 0; phase ^= 1u; }
-                }
+        const bool is_a = warp == 0;
+        const uint32_t afull0 = smem_u32(&bar_afull[0]), aempty0 = smem_u32(&bar_aempty[0]);
+        const uint32_t aend = 8u * p.sa, a_stage = p.a_stage, a_kb = p.a_kb, b_kb = p.b_kb;
+        const int bk = p.bk, kpt = p.kpt, g = p.g;
+        if (!is_a && p.b_resident) {
+            // weights are constants: no grid dependency, the slice is on its way while the previous layer still runs
+            if (leader) {
+                const uint32_t bres = smem_u32(&bar_bres);
+                mbar_expect_tx(bres, static_cast<uint32_t>(p.ntaps * kpt) * b_kb);
+                tma_load_3d(b_ring, &tm_b, bres, 0, ch0, 0);
             }
+            __syncwarp();
         }
-    } else if (warp == 1) {
-        // ------------------------------ weight producer ------------------------------
-        // weights are constants: no grid dependency.  Resident mode loads the CTA's slice once.
-        const bool leader = elect_one2();
-        int slot = 0;
-        uint32_t phase = 0;
-        for (int mt = j0; mt < p.m_tiles; mt += p.gm) {
-            if (p.b_resident && mt != j0) break;
-            if (kHalo) {
-                for (int c = u0; c < u1; ++c)
-                    for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait_spin(smem_u32(&bar_bempty[slot]), phase ^ 1u);
+        if (kHalo) {
+            if (is_a) {
+                pdl_wait2();   // activations are the previous layer's output
+                uint32_t aoff = 0, adst = a_ring, phase = 0;
+                int ti = 0;
+                for (int mt = j0; mt < p.m_tiles; mt += p.gm, ++ti) {
+                    int t = mt;
+                    const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+                    const int tile_h = t % p.tiles_h;
+                    const int tile_n = t / p.tiles_h;
+                    const int ow0 = tile_w * p.tw, oh0 = tile_h * p.th, n0 = tile_n * p.tn;
+                    int cx = p.cin_coff;
+                    for (int c = 0; c < kpt; ++c, cx += bk) {
+                        mbar_wait_spin(aempty0 + aoff, phase ^ 1u);
+                        if (dbg && leader && c == 0 && ti < 7 && !p.dbg_mode) dbg[2 + 8 * ti] = clock64();
                         if (leader) {
-                            const uint32_t full = smem_u32(&bar_bfull[slot]);
-                            mbar_expect_tx(full, p.b_stage);
-                            tma_load_2d(b_ring + slot * p.b_stage, &tm_b, full, tap * p.cin + c * p.bk, ch0);
+                            mbar_expect_tx(afull0 + aoff, p.a_tx);
+                            tma_load_4d(adst, &tm_a, afull0 + aoff, cx, ow0 - 1, oh0 - 1, n0);
                         }
                         __syncwarp();
-                        if (++slot == p.sb) { slot = 0; phase ^= 1u; }
+                        aoff += 8u; adst += a_stage;
+                        if (aoff == aend) { aoff = 0; adst = a_ring; phase ^= 1u; }
                     }
-            } else {
-                for (int u = u0; u < u1; ++u) {
-                    mbar_wait_spin(smem_u32(&bar_bempty[slot]), phase ^ 1u);
+                }
+            } else if (!p.b_resident) {
+                // streamed weights, three taps (one kernel row) per stage; k-block of (tap, chunk c) = tap * kpt + c
+                const uint32_t bfull0 = smem_u32(&bar_bfull[0]), bempty0 = smem_u32(&bar_bempty[0]);
+                const uint32_t bend = 8u * p.sb, b_stage = p.b_stage;
+                uint32_t boff = 0, bdst = b_ring, phase = 0;
+                for (int mt = j0; mt < p.m_tiles; mt += p.gm) {
+                    for (int c = 0; c < kpt; ++c) {
+                        int kb = c;
+                        for (int dy = 0; dy < 3; ++dy) {
+                            mbar_wait_spin(bempty0 + boff, phase ^ 1u);
+                            if (leader) {
+                                mbar_expect_tx(bfull0 + boff, 3u * b_kb);
+                                tma_load_3d(bdst, &tm_b, bfull0 + boff, 0, ch0, kb);
+                                tma_load_3d(bdst + b_kb, &tm_b, bfull0 + boff, 0, ch0, kb + kpt);
+                                tma_load_3d(bdst + 2u * b_kb, &tm_b, bfull0 + boff, 0, ch0, kb + 2 * kpt);
+                            }
+                            __syncwarp();
+                            kb += 3 * kpt;
+                            boff += 8u; bdst += b_stage;
+                            if (boff == bend) { boff = 0; bdst = b_ring; phase ^= 1u; }
+                        }
+                    }
+                }
+            }
+        } else {
+            // per-tap mode: a stage = g k-blocks of activations (+ their weights when the weights stream).  Both warps walk
+            // the same stages; warp 0 arms the barrier and issues the even boxes, warp 1 the weight box and the odd ones.
+            const int nunits = p.ntaps * kpt;
+            const uint32_t stage_tx_b = p.joint ? static_cast<uint32_t>(g) * b_kb : 0u;   // the weight box is always g k-blocks (zero fill past the end)
+            const int parity = is_a ? 0 : 1;
+            bool waited = is_a;
+            if (is_a) pdl_wait2();   // activations are the previous layer's output
+            uint32_t aoff = 0, adst = a_ring, phase = 0;
+            int ti = 0;
+            for (int mt = j0; mt < p.m_tiles; mt += p.gm, ++ti) {
+                int t = mt;
+                const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+                const int tile_h = t % p.tiles_h;
+                const int tile_n = t / p.tiles_h;
+                const int ow0 = tile_w * p.tw, oh0 = tile_h * p.th, n0 = tile_n * p.tn;
+                int tap = 0, kc = 0;
+                int4 tp = s_tap[0];
+                int cx = p.cin_coff + tp.x;
+                for (int u = 0; u < nunits; u += g) {
+                    const int gg = min(g, nunits - u);
+                    mbar_wait_spin(aempty0 + aoff, phase ^ 1u);
+                    if (dbg && leader && is_a && u == 0 && ti < 7 && !p.dbg_mode) dbg[2 + 8 * ti] = clock64();
                     if (leader) {
-                        const uint32_t full = smem_u32(&bar_bfull[slot]);
-                        mbar_expect_tx(full, p.b_stage);
-                        tma_load_2d(b_ring + slot * p.b_stage, &tm_b, full, u * p.bk, ch0);
+                        if (is_a) mbar_expect_tx(afull0 + aoff, static_cast<uint32_t>(gg) * a_kb + stage_tx_b);
+                        else if (p.joint) tma_load_3d(adst + p.b_in_stage, &tm_b, afull0 + aoff, 0, ch0, u);
+                    }
+                    if (!waited && gg > 1) {   // warp 1's first activation box: from here on it reads the previous layer's output
+                        pdl_wait2();
+                        waited = true;
+                    }
+                    uint32_t dst = adst;
+                    for (int j = 0; j < gg; ++j, dst += a_kb) {
+                        if (leader && (j & 1) == parity) tma_load_5d(dst, &tm_a, afull0 + aoff, cx, ow0 + tp.y, tp.z, oh0 + tp.w, n0);
+                        cx += bk;
+                        if (++kc == kpt) {
+                            kc = 0;
+                            ++tap;
+                            tp = s_tap[min(tap, 8)];
+                            cx = p.cin_coff + tp.x;
+                        }
                     }
                     __syncwarp();
-                    if (++slot == p.sb) { slot = 0; phase ^= 1u; }
+                    aoff += 8u; adst += a_stage;
+                    if (aoff == aend) { aoff = 0; adst = a_ring; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 2) {
         // ------------------------------ MMA issuer ------------------------------
+        // One warp feeds the tensor core, so the loop body is what bounds N <= 64 layers: everything a k-block
+        // needs is kept in registers (no parameter loads, no divisions, no 64-bit descriptor rebuilds — a
+        // descriptor is a constant high word and a low word that advances by a constant).
+        // (No tcgen05.fence after the operand barriers: TMA's complete_tx on the mbarrier is what makes the tile
+        // visible to the tensor core, both sides are the async proxy.  The fence stays where TMEM changes hands,
+        // after the accumulator-empty wait.)
         const bool leader = elect_one2();
-        const uint64_t adesc0 = umma_smem_desc(0, p.sbo_a, p.layout);
-        const uint64_t bdesc0 = umma_smem_desc(0, p.sbo_b, p.layout);
-        const int ksteps = p.bk >> 4;
+        const bool resident = p.b_resident != 0;
+        const uint32_t idesc = p.idesc;
+        const bool k4 = p.bk == 64;
+        // descriptor words (umma_smem_desc): lo = addr >> 4 | LBO(1) << 16, hi = SBO >> 4 | version << 14 | layout << 29
+        const uint32_t a_hi = (p.sbo_a >> 4) | (1u << 14) | (p.layout << 29);
+        const uint32_t b_hi = (p.sbo_b >> 4) | (1u << 14) | (p.layout << 29);
+        const uint32_t a_lo0 = (a_ring >> 4) | (1u << 16), b_lo0 = (b_ring >> 4) | (1u << 16);
+        const uint32_t a_step = p.a_stage >> 4, b_step = p.b_stage >> 4;      // per stage
+        const uint32_t a_kb_step = p.a_kb >> 4, b_kb_step = p.b_kb >> 4;      // per k-block
+        const uint32_t b_in_stage = p.b_in_stage >> 4;
+        const uint32_t tap_step = static_cast<uint32_t>(p.kpt) * b_kb_step;   // resident slice: k-blocks in weight order
+        const uint32_t dx_step = p.row_bytes >> 4, dy_step = (static_cast<uint32_t>(p.pw) * p.row_bytes) >> 4;
+        // barrier addresses: base + 8 * slot (the generic -> shared conversion is not free: once per role)
+        const uint32_t afull0 = smem_u32(&bar_afull[0]), aempty0 = smem_u32(&bar_aempty[0]);
+        const uint32_t bfull0 = smem_u32(&bar_bfull[0]), bempty0 = smem_u32(&bar_bempty[0]);
+        const uint32_t accfull0 = smem_u32(&bar_accfull[0]), accempty0 = smem_u32(&bar_accempty[0]);
+        const uint32_t aend = 8u * p.sa, bend = 8u * p.sb;
+        const int g = p.g;
+        auto mma_kblock = [&](uint32_t acc, uint32_t alo, uint32_t blo, uint32_t accumulate) {
+            const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | alo;
+            const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | blo;
+            umma_f16(acc, ad, bd, idesc, accumulate);
+            umma_f16(acc, ad + 2u, bd + 2u, idesc, 1u);
+            if (k4) {
+                umma_f16(acc, ad + 4u, bd + 4u, idesc, 1u);
+                umma_f16(acc, ad + 6u, bd + 6u, idesc, 1u);
+            }
+        };
         uint32_t it = 0;
-        int aslot = 0, bslot = 0;
+        uint32_t aoff = 0, boff = 0;            // 8 * slot
         uint32_t aphase = 0, bphase = 0;
+        uint32_t a_lo = a_lo0, b_lo = b_lo0;
+        if (resident) mbar_wait_spin(smem_u32(&bar_bres), 0u);   // the weight slice is in place
         for (int mt = j0; mt < p.m_tiles; mt += p.gm, ++it) {
             const uint32_t ab = it & 1u;
-            mbar_wait_spin(smem_u32(&bar_accempty[ab]), ((it >> 1) & 1u) ^ 1u);
+            mbar_wait_spin(accempty0 + 8u * ab, ((it >> 1) & 1u) ^ 1u);
             tc_fence_after();
+            if (dbg && leader && it < 7) dbg[3 + 8 * it] = clock64();
             const uint32_t acc = tmem_base + ab * p.acc_stride;
             uint32_t accumulate = 0;
+            if (resident) b_lo = b_lo0;   // resident weights: slot = k-block index
             if (kHalo) {
-                if (p.b_resident) { bslot = 0; bphase = 0; }   // resident weights: slot = k-block index, loaded once
                 for (int c = u0; c < u1; ++c) {
-                    mbar_wait_spin(smem_u32(&bar_afull[aslot]), aphase);
-                    const uint32_t a_addr = a_ring + aslot * p.a_stage;
-                    int dy = 0, dx = 0;
-#pragma unroll 1
-                    for (int tap = 0; tap < 9; ++tap) {
-                        if (!p.b_resident || it == 0) mbar_wait_spin(smem_u32(&bar_bfull[bslot]), bphase);
-                        tc_fence_after();
+                    mbar_wait_spin(afull0 + aoff, aphase);
+                    if (dbg && leader && c == u0 && it < 7) dbg[4 + 8 * it] = clock64();
+                    if (resident) {
+                        // nine k-blocks of MMAs and nothing else; the weight tile of (tap, chunk c) is k-block tap * kpt + c
                         if (leader) {
-                            const uint64_t ad = adesc0 | (((a_addr + (dy * p.pw + dx) * p.row_bytes) & 0x3FFFF) >> 4);
-                            const uint64_t bd = bdesc0 | (((b_ring + bslot * p.b_stage) & 0x3FFFF) >> 4);
-                            if (ksteps == 4) {
+                            uint32_t row_lo = a_lo, w_lo = b_lo;
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) umma_f16(acc, ad + 2u * k, bd + 2u * k, p.idesc, k ? 1u : accumulate);
-                            } else {
+                            for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
-                                for (int k = 0; k < 2; ++k) umma_f16(acc, ad + 2u * k, bd + 2u * k, p.idesc, k ? 1u : accumulate);
+                                for (int dx = 0; dx < 3; ++dx) {
+                                    mma_kblock(acc, row_lo + dx * dx_step, w_lo, accumulate);
+                                    accumulate = 1;
+                                    w_lo += tap_step;
+                                }
+                                row_lo += dy_step;
                             }
-                            if (!p.b_resident) umma_commit(smem_u32(&bar_bempty[bslot]));
-                            if (tap == 8) umma_commit(smem_u32(&bar_aempty[aslot]));   // patch consumed
+                            umma_commit(aempty0 + aoff);   // patch consumed
                         }
                         __syncwarp();
                         accumulate = 1;
-                        if (++dx == 3) { dx = 0; ++dy; }
-                        if (++bslot == p.sb) { bslot = 0; bphase ^= 1u; }
+                        b_lo += b_kb_step;   // next chunk
+                    } else {
+                        uint32_t row_lo = a_lo;
+#pragma unroll 1
+                        for (int dy = 0; dy < 3; ++dy) {
+                            mbar_wait_spin(bfull0 + boff, bphase);   // the three taps of this kernel row
+                            if (leader) {
+#pragma unroll
+                                for (int dx = 0; dx < 3; ++dx) {
+                                    mma_kblock(acc, row_lo + dx * dx_step, b_lo + dx * b_kb_step, accumulate);
+                                    accumulate = 1;
+                                }
+                                umma_commit(bempty0 + boff);
+                                if (dy == 2) umma_commit(aempty0 + aoff);   // patch consumed
+                            }
+                            __syncwarp();
+                            accumulate = 1;
+                            row_lo += dy_step;
+                            b_lo += b_step;
+                            boff += 8u;
+                            if (boff == bend) { boff = 0; bphase ^= 1u; b_lo = b_lo0; }
+                        }
                     }
-                    if (++aslot == p.sa) { aslot = 0; aphase ^= 1u; }
+                    a_lo += a_step;
+                    aoff += 8u;
+                    if (aoff == aend) { aoff = 0; aphase ^= 1u; a_lo = a_lo0; }
                 }
             } else {
-                if (p.b_resident) { bslot = 0; bphase = 0; }
 #pragma unroll 1
-                for (int u = u0; u < u1; ++u) {
-                    if (!p.b_resident || it == 0) mbar_wait_spin(smem_u32(&bar_bfull[bslot]), bphase);
-                    mbar_wait_spin(smem_u32(&bar_afull[aslot]), aphase);
-                    tc_fence_after();
+                for (int u = u0; u < u1; u += g) {
+                    const int gg = min(g, u1 - u);
+                    mbar_wait_spin(afull0 + aoff, aphase);
+                    if (dbg && leader && u == u0 && it < 7) dbg[4 + 8 * it] = clock64();
                     if (leader) {
-                        const uint64_t ad = adesc0 | (((a_ring + aslot * p.a_stage) & 0x3FFFF) >> 4);
-                        const uint64_t bd = bdesc0 | (((b_ring + bslot * p.b_stage) & 0x3FFFF) >> 4);
-                        if (ksteps == 4) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) umma_f16(acc, ad + 2u * k, bd + 2u * k, p.idesc, k ? 1u : accumulate);
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 2; ++k) umma_f16(acc, ad + 2u * k, bd + 2u * k, p.idesc, k ? 1u : accumulate);
+                        uint32_t alo = a_lo, blo = resident ? b_lo : a_lo + b_in_stage;
+                        for (int j = 0; j < gg; ++j) {
+                            mma_kblock(acc, alo, blo, accumulate);
+                            accumulate = 1;
+                            alo += a_kb_step;
+                            blo += b_kb_step;
                         }
-                        umma_commit(smem_u32(&bar_aempty[aslot]));
-                        if (!p.b_resident) umma_commit(smem_u32(&bar_bempty[bslot]));
+                        umma_commit(aempty0 + aoff);
                     }
                     __syncwarp();
                     accumulate = 1;
-                    if (++aslot == p.sa) { aslot = 0; aphase ^= 1u; }
-                    if (++bslot == p.sb) { bslot = 0; bphase ^= 1u; }
+                    b_lo += static_cast<uint32_t>(gg) * b_kb_step;
+                    a_lo += a_step;
+                    aoff += 8u;
+                    if (aoff == aend) { aoff = 0; aphase ^= 1u; a_lo = a_lo0; }
                 }
             }
-            if (leader) umma_commit(smem_u32(&bar_accfull[ab]));   // accumulator of this tile complete
+            if (leader) umma_commit(accfull0 + 8u * ab);   // accumulator of this tile complete
+            if (dbg && leader && it < 7) dbg[5 + 8 * it] = clock64();
+            __syncwarp();
+        }
+    } else if (warp == 3) {
+        // ------------------------------ epilogue DMA (TMA epilogue only) ------------------------------
+        // Shortcut tiles in, output tiles out, one 32-column sub-tile at a time.  The epilogue warps never touch
+        // global memory: a row-per-thread tile moved with 16-byte accesses costs one L1 request per thread and
+        // instruction (16 N cycles per tile for the stores alone, profiles/r2_timeline_v2.txt); through shared
+        // memory it is 2 N cycles of conflict-free STS and one bulk store the TMA unit turns into full lines.
+        if (p.tma_epi) {
+            const bool leader = elect_one2();
+            const bool has_res = kRes && p.res != nullptr;
+            const uint32_t stage = smem_base + p.stage_off;
+            const uint32_t outready0 = smem_u32(&bar_outready[0]), stfree0 = smem_u32(&bar_stfree[0]), resfull0 = smem_u32(&bar_resfull[0]);
+            const uint32_t res_bytes = 128u * 64u;   // [128 rows][32 fp16]
+            pdl_wait2();   // shortcut reads and output writes must follow the previous grid
+            auto coords = [&](int mt, int& ow0, int& oh0, int& n0) {
+                int t = mt;
+                const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+                const int tile_h = t % p.tiles_h;
+                const int tile_n = t / p.tiles_h;
+                ow0 = tile_w * p.tw; oh0 = tile_h * p.th; n0 = tile_n * p.tn;
+            };
+            int ow0, oh0, n0;
+            if (has_res && j0 < p.m_tiles) {
+                coords(j0, ow0, oh0, n0);
+                if (leader)
+                    for (int sidx = 0; sidx < p.nchunks; ++sidx) {
+                        mbar_expect_tx(resfull0 + 8u * sidx, res_bytes);
+                        tma_load_4d(stage + sidx * p.sub_bytes, &tm_res, resfull0 + 8u * sidx, p.res_coff + ch0 + 32 * sidx, ow0, oh0, n0);
+                    }
+                __syncwarp();
+            }
+            uint32_t it = 0;
+            for (int mt = j0; mt < p.m_tiles; mt += p.gm, ++it) {
+                coords(mt, ow0, oh0, n0);
+                int nw0 = 0, nh0 = 0, nn0 = 0;
+                const bool more = mt + p.gm < p.m_tiles;
+                if (more) coords(mt + p.gm, nw0, nh0, nn0);
+                for (int sidx = 0; sidx < p.nchunks; ++sidx) {
+                    mbar_wait_spin(outready0 + 8u * sidx, it & 1u);
+                    if (leader) {
+                        const uint32_t src = stage + sidx * p.sub_bytes;
+                        tma_store_4d(&tm_out, src, p.out_coff + ch0 + 32 * sidx, ow0, oh0, n0);
+                        if (p.dup_mode == 1) {
+                            tma_store_4d(&tm_dup.m[0], src, p.dup_coff + ch0 + 32 * sidx, ow0, oh0, n0);
+                        } else if (p.dup_mode == 2) {
+                            // nearest 2x upsample written by the producer: phase (dy, dx) of the destination is a strided
+                            // view with the source's extents, so the same box lands on pixels (2 oh + dy, 2 ow + dx)
+#pragma unroll
+                            for (int ph = 0; ph < 4; ++ph) tma_store_4d(&tm_dup.m[ph], src, p.dup_coff + ch0 + 32 * sidx, ow0, oh0, n0);
+                        }
+                        bulk_commit_group();
+                        bulk_wait_read0();   // the sub-tile has been read out: it may be refilled
+                        if (has_res) {
+                            if (more) {
+                                mbar_expect_tx(resfull0 + 8u * sidx, res_bytes);
+                                tma_load_4d(src, &tm_res, resfull0 + 8u * sidx, p.res_coff + ch0 + 32 * sidx, nw0, nh0, nn0);
+                            }
+                        } else {
+                            mbar_arrive(stfree0 + 8u * sidx);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (leader) bulk_wait_all();   // the global writes are complete before the CTA retires
             __syncwarp();
         }
     } else if (warp >= 4) {
@@ -309,7 +501,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         const int nvalid = min(p.block_n, p.cout - ch0);
         const bool vec = p.vec_ok != 0;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        pdl_wait2();   // residual reads and output writes must follow the previous grid
+        if (!p.tma_epi) pdl_wait2();   // residual reads and output writes must follow the previous grid
         uint32_t it = 0;
         for (int mt = j0; mt < p.m_tiles; mt += p.gm, ++it) {
             int t = mt;
@@ -429,10 +621,99 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
 
             mbar_wait_spin(smem_u32(&bar_accfull[ab]), (it >> 1) & 1);
             tc_fence_after();
+            if (dbg && threadIdx.x == 128 && it < 7 && !p.dbg_mode) dbg[6 + 8 * it] = clock64();
             // the last chunk this warp reads: once it is in registers the accumulator goes back to the issuer
             int last_c0 = -1;
             for (int c0 = chunk0; c0 < nvalid; c0 += 64) last_c0 = c0;
-            if (p.splits == 1) {
+            if (p.tma_epi) {
+                // ---- TMA epilogue: accumulator chunk -> registers -> (+ shortcut from the staged tile) -> staging
+                // sub-tile in the swizzled layout the bulk store expects -> warp 3 stores it ----
+                const bool has_res = kRes && p.res != nullptr;
+                const uint32_t stage = smem_base + p.stage_off;
+                const bool f32out = p.out_f32 != 0;
+                // 16-byte slot j of row `row` sits at j ^ swz: SWIZZLE_64B rows (fp16, 64 B) / SWIZZLE_128B rows (fp32, 128 B)
+                const uint32_t swz = f32out ? static_cast<uint32_t>(row & 7) : static_cast<uint32_t>((row >> 1) & 3);
+                const uint32_t row_off = static_cast<uint32_t>(row) * p.chunk_bytes;
+                for (int c0 = chunk0; c0 < nvalid; c0 += 64) {
+                    const int sidx = c0 >> 5;
+                    uint32_t v[32];
+                    __syncwarp();
+                    tmem_ld_32(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (c0 == last_c0) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&bar_accempty[ab]));
+                        if (dbg && threadIdx.x == 128 && it < 7 && !p.dbg_mode) dbg[7 + 8 * it] = clock64();
+                    }
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
+                    if (p.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float h = 0.5f * f[j];
+                            f[j] = fmaf(h, tanh_approx(h), h);
+                        }
+                    } else if (p.act == 2) {
+#pragma unroll
+                        for (int h0 = 0; h0 < 32; h0 += 16) {
+                            float e[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) e[j] = 1.0f + ex2_approx(-1.4426950408889634f * f[h0 + j]);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[h0 + j] = f[h0 + j] * rcp_approx2(e[j]);
+                        }
+                    }
+                    const uint32_t sub = stage + sidx * p.sub_bytes + row_off;
+                    if (has_res) {
+                        mbar_wait_spin(smem_u32(&bar_resfull[sidx]), it & 1u);   // the shortcut tile landed (and the sub-tile is ours)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 r;
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                                         : "r"(sub + ((static_cast<uint32_t>(j) ^ swz) << 4)));
+                            const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float2 a = __half22float2(h[u]);
+                                f[8 * j + 2 * u] += a.x; f[8 * j + 2 * u + 1] += a.y;
+                            }
+                        }
+                    } else {
+                        mbar_wait_spin(smem_u32(&bar_stfree[sidx]), (it & 1u) ^ 1u);   // the previous tile's store has read it out
+                    }
+                    if (f32out) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sub + ((static_cast<uint32_t>(j) ^ swz) << 4)),
+                                         "f"(f[4 * j]), "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3]) : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const __half2 hh = __floats2half2_rn(f[8 * j + 2 * u], f[8 * j + 2 * u + 1]);
+                                w[u] = *reinterpret_cast<const uint32_t*>(&hh);
+                            }
+                            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sub + ((static_cast<uint32_t>(j) ^ swz) << 4)),
+                                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                        }
+                    }
+                    fence_proxy_async();   // generic-proxy writes -> visible to the bulk store
+                    mbar_arrive(smem_u32(&bar_outready[sidx]));
+                }
+                if (dbg && it < 7 && !p.dbg_mode) {
+                    if (threadIdx.x == 128) dbg[8 + 8 * it] = clock64();
+                    if (threadIdx.x == 256) dbg[9 + 8 * it] = clock64();
+                }
+                if (last_c0 < 0) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bar_accempty[ab]));
+                }
+            } else {
                 for (int c0 = chunk0; c0 < nvalid; c0 += 64) {
                     uint32_t v[32];
                     __syncwarp();   // tcgen05.ld is warp-aligned: reconverge after the predicated stores
@@ -443,67 +724,22 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&bar_accempty[ab]));
+                        if (dbg && threadIdx.x == 128 && it < 7 && !p.dbg_mode) dbg[7 + 8 * it] = clock64();
                     }
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                     if (valid) finish_chunk(c0, f);
                 }
+                if (dbg && it < 7 && !p.dbg_mode) {
+                    if (threadIdx.x == 128) dbg[8 + 8 * it] = clock64();
+                    if (threadIdx.x == 256) dbg[9 + 8 * it] = clock64();
+                }
                 if (last_c0 < 0) {   // this warp has no chunk (N <= 32 and warp >= 8): still release the buffer
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&bar_accempty[ab]));
                 }
-            } else {
-                // ---- split-K: every split parks its raw fp32 partial tile; the split that arrives last sums
-                // them in split order (deterministic) and runs the real epilogue ----
-                const size_t tile_lin = static_cast<size_t>(nt) * p.m_tiles + mt;
-                float* part = p.partial + (tile_lin * p.splits * 128 + row) * p.part_ld;
-                const size_t split_stride = static_cast<size_t>(128) * p.part_ld;
-                for (int c0 = chunk0; c0 < nvalid; c0 += 64) {
-                    uint32_t v[32];
-                    __syncwarp();
-                    tmem_ld_32(taddr + c0, v);
-                    tmem_ld_wait();
-                    if (valid) {
-                        float4* o = reinterpret_cast<float4*>(part + split * split_stride + c0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bar_accempty[ab]));
-                asm volatile("bar.sync 1, 256;" ::: "memory");   // the epilogue warps: all partial stores issued
-                if (threadIdx.x == 128) {
-                    __threadfence();   // cumulative: publishes the CTA's stores ordered before it by the barrier
-                    s_last = (atomicAdd(p.counters + tile_lin, 1) == p.splits - 1) ? 1 : 0;
-                    __threadfence();
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (s_last) {
-                    for (int c0 = chunk0; c0 < nvalid; c0 += 64) {
-                        fetch_res(c0);
-                        if (valid) {
-                            float f[32];
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] = 0.f;
-                            for (int z = 0; z < p.splits; ++z) {
-                                const float4* src = reinterpret_cast<const float4*>(part + z * split_stride + c0);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float4 tv = __ldcg(src + j);
-                                    f[4 * j] += tv.x; f[4 * j + 1] += tv.y; f[4 * j + 2] += tv.z; f[4 * j + 3] += tv.w;
-                                }
-                            }
-                            finish_chunk(c0, f);
-                        }
-                    }
-                    if (threadIdx.x == 128) p.counters[tile_lin] = 0;   // ready for the next launch of this layer
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");   // s_last is rewritten by the next tile
             }
         }
         __syncwarp();
@@ -511,6 +747,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
 
     tc_fence_before();
     __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[60] = clock64();
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
@@ -545,9 +782,9 @@ EncodeTiledFn2 encode_fn2() {
     return fn;
 }
 void encode2(CUtensorMap* tm, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-             const cuuint32_t* box, CUtensorMapSwizzle swz) {
+             const cuuint32_t* box, CUtensorMapSwizzle swz, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16) {
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode_fn2()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, dims, strides_bytes, box, estr,
+    CUresult r = encode_fn2()(tm, dtype, rank, base, dims, strides_bytes, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
@@ -614,13 +851,22 @@ void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
     const int kb_per_unit = p.halo ? 9 : 1;
     const int ksteps = p.bk / 16;
     const int force_n = env_int("RMR_CONV_N", 0);
-    const int force_splits = env_int("RMR_CONV_SPLITS", 0);
+    const int force_splits = 0;
+    // TMA epilogue (shared-memory staged tile, bulk store): whole 32-channel chunks, 16-byte aligned views, one
+    // destination or a plain second copy; the 2x-upsample destination and ragged channel counts keep the direct stores
+    const int out_align0 = d.out_f32 ? 4 : 8;
+    const bool views_ok = d.out_pitch % out_align0 == 0 && d.out_coff % out_align0 == 0 &&
+                          (d.res == nullptr || (d.res_pitch % 8 == 0 && d.res_coff % 8 == 0 && !d.out_f32)) &&
+                          (d.dup == nullptr || (d.dup_pitch % 8 == 0 && d.dup_coff % 8 == 0 && !d.out_f32));
+    const bool tma_epi_ok = env_flag("RMR_TMA_EPI", true) && views_ok && d.cout % 32 == 0 && d.cout == d.cout_pad && force_splits <= 1;
+    const int esize = d.out_f32 ? 4 : 2;
     const int kSM = 148;
     double best_cost = -1;
     int best_n = 0, best_splits = 1;
     for (int bn = 256; bn >= 16; bn -= 16) {
         if (d.cout_pad % bn != 0) continue;
         if (force_n && bn != force_n && d.cout_pad % force_n == 0) continue;
+        if (tma_epi_ok && bn % 32 != 0) continue;
         const int n_tiles = d.cout_pad / bn;
         // split-K (deterministic: fp32 partial tiles through L2, last-arriving split reduces) stays available for
         // experiments (RMR_CONV_SPLITS=n) but is not planned: a partial tile is 128 x N x 4 B written and read
@@ -628,7 +874,7 @@ void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
         // 40x40x256 -> 384 stride 2 at batch 7, 8 splits: 228 us against 25 us for the round-1 kernel).  Narrower
         // channel tiles give the small maps their parallelism instead: below N = 64 an MMA costs the same ~56
         // issue cycles whatever N is, so more, narrower CTAs are free until the activation re-reads show.
-        const int max_splits = force_splits ? force_splits : 1;
+        const int max_splits = 1;
         for (int splits = 1; splits <= max_splits; ++splits) {
             if (force_splits && splits != force_splits && units >= force_splits) continue;
             const int ups = (units + splits - 1) / splits;
@@ -646,7 +892,9 @@ void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
             //   smem    (A 4096 B + B 32 N B read by the MMA + bytes TMA writes for the slice) / 128 B/clk
             //   ingest  L2 -> SM: 125 B/clk for a lone SM, ~75 B/clk per SM when all 148 stream
             const double a_write = p.halo ? 4096.0 * (18.0 * p.pw) / (9.0 * 128.0) : 4096.0;
-            const bool resident = static_cast<double>(kb) * bn * p.bk * 2 + (p.halo ? 2.0 : 4.0) * 16384 <= kSmemMax - 1024 && kb <= kMaxB;
+            const double staging = tma_epi_ok ? 128.0 * bn * esize : 0.0;
+            const bool resident = static_cast<double>(kb) * bn * p.bk * 2 + (p.halo ? 2.0 : 3.0) * 16384 + staging <= kSmemMax - 1024 &&
+                                  (p.halo || tiles_per_cta > 1);
             const double b_write = resident ? bn * 32.0 / tiles_per_cta : bn * 32.0;
             const double smem_cyc = (4096.0 + bn * 32.0 + a_write + b_write) / 128.0;
             const double ingest_rate = std::min(125.0, 11000.0 / busy);
@@ -654,7 +902,9 @@ void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
             const double per_kb = ksteps * slice;
             // epilogue of one tile: 8 warps, 32-column chunks (TMEM load, bias, SiLU, fp16 stores); overlaps the next
             // tile's main loop, so a tile costs the larger of the two
-            const double epi = 500.0 + (bn > 64 ? (bn - 64) * 7.0 : 0.0) + (splits > 1 ? 4000.0 + bn * 30.0 * splits : 0.0);
+            // (direct stores: one L1 request per thread and 16 bytes, 16 N cycles for an fp16 tile)
+            const double epi = (tma_epi_ok ? 500.0 + bn * 4.0 : 400.0 + bn * 8.0 * esize * (d.res ? 2.0 : 1.0)) +
+                               (splits > 1 ? 4000.0 + bn * 30.0 * splits : 0.0);
             const double tile_cyc = std::max(kb * per_kb, epi);
             // per-CTA fixed cost: launch ramp, barrier init, TMEM allocation, first operands in flight, last epilogue
             const double cost = waves * (2400.0 + tiles_per_cta * tile_cyc + epi);
@@ -670,41 +920,62 @@ void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
     p.gm = static_cast<int>(std::max<long>(1, std::min<long>(p.m_tiles, kSM / std::max(1, std::min(p.ns_total, kSM)))));
     const int kb_cta = p.units_per_split * kb_per_unit;
 
-    // ---- shared-memory layout: [A ring][B slots] ----
-    p.b_stage = static_cast<uint32_t>(p.block_n) * p.bk * 2u;
+    // ---- shared-memory layout: [A (or joint) ring][weights: resident slice | halo stream ring][epilogue staging] ----
+    p.b_kb = static_cast<uint32_t>(p.block_n) * p.bk * 2u;
     if (p.halo) {
         p.a_tx = 18u * p.pw * p.row_bytes;
-        p.a_stage = (p.a_tx + 1023u) & ~1023u;
+        p.a_kb = (p.a_tx + 1023u) & ~1023u;
     } else {
         p.a_tx = 128u * p.row_bytes;
-        p.a_stage = p.a_tx;
+        p.a_kb = p.a_tx;
     }
-    const int budget = kSmemMax - 1024;
+    p.tma_epi = (tma_epi_ok && p.splits == 1) ? 1 : 0;
+    p.esize_out = esize;
+    p.nchunks = p.block_n / 32;
+    p.chunk_bytes = 32u * esize;
+    p.sub_bytes = 128u * p.chunk_bytes;
+    const int stage_bytes = p.tma_epi ? static_cast<int>(p.sub_bytes) * p.nchunks : 0;
+    const long budget = kSmemMax - 1024 - stage_bytes;
     const int tiles_per_cta = (p.m_tiles + p.gm - 1) / p.gm;
-    const int a_units_total = tiles_per_cta * p.units_per_split;          // A stages this CTA ever loads
-    const int a_min = std::min(a_units_total, p.halo ? 2 : 4);
-    p.b_resident = (kb_cta <= kMaxB && static_cast<long>(kb_cta) * p.b_stage + static_cast<long>(a_min) * p.a_stage <= budget &&
-                    env_flag("RMR_B_RESIDENT", true)) ? 1 : 0;
-    if (p.b_resident) {
-        p.sb = kb_cta;
-        p.sa = static_cast<int>(std::min<long>({kMaxA, a_units_total, (budget - static_cast<long>(p.sb) * p.b_stage) / p.a_stage}));
-    } else {
-        // streaming weights.  Halo mode: two or three patch slots, the rest of the budget is weight slots;
-        // per-tap mode: A and B are consumed in lock step, so both rings cover the same number of k-blocks.
-        const long total_kb = static_cast<long>(kb_cta) * tiles_per_cta;
-        if (p.halo) {
-            const long a_res = static_cast<long>(std::min(a_units_total, 3)) * p.a_stage;
-            p.sb = static_cast<int>(std::max<long>(2, std::min<long>({kMaxB, (budget - a_res) / p.b_stage, total_kb})));
+    const long a_units_total = static_cast<long>(tiles_per_cta) * p.units_per_split;   // A units (patches / k-blocks) this CTA ever loads
+    const long b_slice = static_cast<long>(kb_cta) * p.b_kb;
+    const bool want_resident = env_flag("RMR_B_RESIDENT", true);
+    long b_region = 0;
+    p.g = 1; p.joint = 0; p.b_in_stage = 0; p.sb = 0; p.b_stage = p.b_kb;
+    if (p.halo) {
+        p.a_stage = p.a_kb;
+        p.b_resident = (want_resident && b_slice + std::min<long>(a_units_total, 2) * p.a_stage <= budget) ? 1 : 0;
+        if (p.b_resident) {
+            b_region = b_slice;
         } else {
-            p.sb = static_cast<int>(std::max<long>(2, std::min<long>({kMaxB, budget / (p.a_stage + p.b_stage), total_kb})));
+            // streamed weights: three taps (one kernel row) per stage; two or three patch slots, the rest is weight stages
+            p.b_stage = 3u * p.b_kb;
+            const long a_res = std::min<long>(a_units_total, 3) * p.a_stage;
+            p.sb = static_cast<int>(std::max<long>(2, std::min<long>({kMaxB, (budget - a_res) / p.b_stage, 3 * a_units_total})));
+            b_region = static_cast<long>(p.sb) * p.b_stage;
         }
-        p.sa = static_cast<int>(std::max<long>(1, std::min<long>({kMaxA, a_units_total, (budget - static_cast<long>(p.sb) * p.b_stage) / p.a_stage})));
+        p.sa = static_cast<int>(std::max<long>(1, std::min<long>({kMaxA, a_units_total, (budget - b_region) / p.a_stage})));
+    } else {
+        // a CTA with one tile has nothing to reuse: its weights stream in the activation stages (joint ring, one
+        // barrier per stage); with several tiles the slice stays resident when it fits
+        p.b_resident = (want_resident && tiles_per_cta > 1 && b_slice + 3L * p.a_kb <= budget) ? 1 : 0;
+        const long kb_bytes = p.a_kb + (p.b_resident ? 0 : p.b_kb);
+        b_region = p.b_resident ? b_slice : 0;
+        p.joint = p.b_resident ? 0 : 1;
+        // k-blocks per stage: as many as leave three stages in flight, at most four
+        p.g = static_cast<int>(std::max<long>(1, std::min<long>({4, kb_cta, (budget - b_region) / (3 * kb_bytes)})));
+        if (const int fg = env_int("RMR_CONV_G", 0)) p.g = std::max(1, std::min(fg, kb_cta));
+        p.a_stage = static_cast<uint32_t>(p.g * kb_bytes);
+        p.b_in_stage = static_cast<uint32_t>(p.g) * p.a_kb;
+        const long stages_total = static_cast<long>(tiles_per_cta) * ((kb_cta + p.g - 1) / p.g);
+        p.sa = static_cast<int>(std::max<long>(1, std::min<long>({kMaxA, stages_total, (budget - b_region) / p.a_stage})));
     }
-    if (p.sa < 1 || static_cast<long>(p.sa) * p.a_stage + static_cast<long>(p.sb) * p.b_stage > budget)
+    if (static_cast<long>(p.sa) * p.a_stage + b_region > budget)
         throw CudaError("conv2: operand ring does not fit in shared memory");
     p.a_off = 0;
     p.b_off = static_cast<uint32_t>(p.sa) * p.a_stage;
-    l.smem_bytes = static_cast<int>(p.b_off + static_cast<uint32_t>(p.sb) * p.b_stage) + 1024;
+    p.stage_off = p.b_off + static_cast<uint32_t>(b_region);   // 1 KB aligned: every stage is a multiple of 1 KB
+    l.smem_bytes = static_cast<int>(p.stage_off) + stage_bytes + 1024;
 
     p.acc_stride = static_cast<uint32_t>((p.block_n + 31) / 32 * 32);
     const uint32_t need = 2 * p.acc_stride;
@@ -759,11 +1030,42 @@ void make_conv2_launch(const ConvDesc& d, ConvLaunch& l) {
         encode2(&l.tm_a, const_cast<__half*>(d.in), 5, dims, strides, box, swz);
     }
     {
+        // weights [Cout_pad][K] as (bk, Cout_pad, K / bk): k-block outermost, so a box of several k-blocks lands as
+        // consecutive [N][bk] UMMA tiles.  Box depth: the whole slice (resident), g k-blocks (joint ring) or one
         const cuuint64_t ktot = static_cast<cuuint64_t>(p.ntaps) * d.cin_pad;
-        cuuint64_t dims[2] = {ktot, static_cast<cuuint64_t>(d.cout_pad)};
-        cuuint64_t strides[1] = {ktot * 2};
-        cuuint32_t box[2] = {static_cast<cuuint32_t>(p.bk), static_cast<cuuint32_t>(p.block_n)};
-        encode2(&l.tm_b, const_cast<__half*>(d.w), 2, dims, strides, box, swz);
+        const int kb_total = p.ntaps * p.kpt;
+        const int depth = p.b_resident ? kb_total : (p.halo ? 1 : p.g);
+        cuuint64_t dims[3] = {static_cast<cuuint64_t>(p.bk), static_cast<cuuint64_t>(d.cout_pad), static_cast<cuuint64_t>(kb_total)};
+        cuuint64_t strides[2] = {ktot * 2, static_cast<cuuint64_t>(p.bk) * 2};
+        cuuint32_t box[3] = {static_cast<cuuint32_t>(p.bk), static_cast<cuuint32_t>(p.block_n), static_cast<cuuint32_t>(depth)};
+        encode2(&l.tm_b, const_cast<__half*>(d.w), 3, dims, strides, box, swz);
+    }
+    if (p.tma_epi) {
+        // output / shortcut / second destination: (C, W, H, N) views, box = one 32-channel sub-tile of the pixel tile
+        auto view = [&](CUtensorMap* tm, void* base, int pitch, bool f32) {
+            const cuuint64_t es = f32 ? 4 : 2, cpi = static_cast<cuuint64_t>(pitch);
+            cuuint64_t dims[4] = {cpi, static_cast<cuuint64_t>(d.w_out), static_cast<cuuint64_t>(d.h_out), static_cast<cuuint64_t>(d.n)};
+            cuuint64_t strides[3] = {cpi * es, d.w_out * cpi * es, static_cast<cuuint64_t>(d.h_out) * d.w_out * cpi * es};
+            cuuint32_t box[4] = {32u, static_cast<cuuint32_t>(p.tw), static_cast<cuuint32_t>(p.th), static_cast<cuuint32_t>(p.tn)};
+            encode2(tm, base, 4, dims, strides, box, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+        };
+        view(&l.tm_out, d.out, d.out_pitch, d.out_f32 != 0);
+        if (d.res) view(&l.tm_res, const_cast<__half*>(d.res), d.res_pitch, false);
+        if (d.dup && d.dup_mode == 1) view(&l.tm_dup[0], d.dup, d.dup_pitch, false);
+        if (d.dup && d.dup_mode == 2) {
+            // destination [N][2H][2W][pitch]: phase (dy, dx) = base + (dy * 2W + dx) pixels, pixel steps doubled
+            const cuuint64_t cpi = static_cast<cuuint64_t>(d.dup_pitch);
+            for (int ph = 0; ph < 4; ++ph) {
+                const int dy = ph >> 1, dx = ph & 1;
+                __half* base = d.dup + (static_cast<size_t>(dy) * 2 * d.w_out + dx) * d.dup_pitch;
+                cuuint64_t dims[4] = {cpi, static_cast<cuuint64_t>(d.w_out), static_cast<cuuint64_t>(d.h_out), static_cast<cuuint64_t>(d.n)};
+                cuuint64_t strides[3] = {2 * cpi * 2, 2 * (2 * static_cast<cuuint64_t>(d.w_out)) * cpi * 2,
+                                         (2 * static_cast<cuuint64_t>(d.h_out)) * (2 * d.w_out) * cpi * 2};
+                cuuint32_t box[4] = {32u, static_cast<cuuint32_t>(p.tw), static_cast<cuuint32_t>(p.th), static_cast<cuuint32_t>(p.tn)};
+                encode2(&l.tm_dup[ph], base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+            }
+        }
     }
 }
 
@@ -818,12 +1120,14 @@ void launch_conv2(const ConvLaunch& l, cudaStream_t s, bool pdl) {
     cfg.attrs = attr;
     cfg.numAttrs = na;
     const bool res = l.q.res != nullptr;
+    DupMaps dm;
+    std::memcpy(dm.m, l.tm_dup, sizeof(dm.m));
     if (l.q.halo) {
-        if (res) RMR_CUDA((cudaLaunchKernelEx(&cfg, conv2_kernel<true, true>, l.tm_a, l.tm_b, l.q)));
-        else RMR_CUDA((cudaLaunchKernelEx(&cfg, conv2_kernel<true, false>, l.tm_a, l.tm_b, l.q)));
+        if (res) RMR_CUDA((cudaLaunchKernelEx(&cfg, conv2_kernel<true, true>, l.tm_a, l.tm_b, l.tm_out, l.tm_res, dm, l.q)));
+        else RMR_CUDA((cudaLaunchKernelEx(&cfg, conv2_kernel<true, false>, l.tm_a, l.tm_b, l.tm_out, l.tm_res, dm, l.q)));
     } else {
-        if (res) RMR_CUDA((cudaLaunchKernelEx(&cfg, conv2_kernel<false, true>, l.tm_a, l.tm_b, l.q)));
-        else RMR_CUDA((cudaLaunchKernelEx(&cfg, conv2_kernel<false, false>, l.tm_a, l.tm_b, l.q)));
+        if (res) RMR_CUDA((cudaLaunchKernelEx(&cfg, conv2_kernel<false, true>, l.tm_a, l.tm_b, l.tm_out, l.tm_res, dm, l.q)));
+        else RMR_CUDA((cudaLaunchKernelEx(&cfg, conv2_kernel<false, false>, l.tm_a, l.tm_b, l.tm_out, l.tm_res, dm, l.q)));
     }
 }
 

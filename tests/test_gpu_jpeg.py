@@ -120,6 +120,17 @@ def test_rejects_unsupported_and_flags_corrupt_streams(decoder):
     cut = good[:len(good) // 2] + b"\xff\xd9"
     with pytest.raises(rr.RadarError, match="corrupt"):
         decoder.decode(cut)
+    # over-subscribed Huffman table (a DHT whose code-length counts break the Kraft bound, e.g. 255 codes of
+    # length 1): must be rejected before any table entry is written (it used to index far past the lookup table)
+    i = good.index(b"\xff\xc4")
+    bad_dht = bytearray(good)
+    bits = bad_dht[i + 5:i + 21]                  # marker(2) length(2) class/id(1) then bits[1..16]
+    donor = max(range(16), key=lambda l: bits[l])
+    assert bits[donor] >= 3
+    bad_dht[i + 5 + donor] -= 3                   # same symbol count, so the segment length still parses
+    bad_dht[i + 5] += 3                           # three codes of length 1: only two exist
+    with pytest.raises(ValueError, match="Huffman"):
+        decoder.decode(bytes(bad_dht))
     # and the decoder is still usable afterwards
     check(decoder, good, jo.decode(good), "after errors")
 
