@@ -197,6 +197,56 @@ def config_dict(world):
             "parallelism": f"dp{world} (stream per GPU)"}
 
 
+def throughput_leg(torch, rr, fx, dev, local_rank, stream, loc_stream, bg, cloud, peak_tf, frames=16, size=1280, steps=10, warmup=3):
+    """BASELINE config[2]: `frames` camera + LiDAR streams per step (rmr_run_batch): the car network batched over the
+    frames, the armor network over all their ROIs, one Locator per stream.  Inputs resident in HBM, two batches rotated
+    (2 x 79 MB of frames > L2)."""
+    import cv2
+    img = cv2.resize(fx.load_frame(0), (size, size), interpolation=cv2.INTER_LINEAR)
+    det = rr.RobotDetector(fx.engine("car"), fx.engine("armor"), (size, size), fx.CLASS_NUM, fx.MAX_BATCH, fx.OPT_BATCH,
+                           device=local_rank, frames=frames)
+    det.set_stream(stream.cuda_stream)
+    locs = []
+    for _ in range(frames):
+        loc = rr.Locator(size, size, fx.scaled_intrinsic(size, size), fx.LIDAR_TO_CAMERA, fx.WORLD_TO_CAMERA, device=local_rank)
+        loc.set_stream(loc_stream.cuda_stream)
+        loc.update(bg[: 1 << 20])
+        locs.append(loc)
+    pool = 2
+    fr = torch.from_numpy(np.ascontiguousarray(img)).to(dev).unsqueeze(0).repeat(pool * frames, 1, 1, 1).contiguous()
+    cl = torch.from_numpy(cloud).to(dev).unsqueeze(0).repeat(pool * frames, 1, 1).contiguous()
+    npts = cloud.shape[0]
+
+    def step(i):
+        j = (i % pool) * frames
+        loc_stream.wait_stream(stream)
+        return rr.run_batch_records(det, locs, fr[j].data_ptr(), True, frames, size, size, size * 3, cl[j].data_ptr(), True, npts, 12)
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    car_ms = armor_ms = 0.0
+    e0.record(stream)
+    for i in range(steps):
+        recs, counts = step(warmup + i)
+        t = det.last_timing()
+        car_ms += t[0]; armor_ms += t[1]
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    st = det.last_stats()
+    conv_ms = (car_ms + armor_ms) / steps
+    tf = st["conv_flops"] / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    return {"value": frames * steps / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms / steps, "frames_per_step": frames,
+            "workload": f"BASELINE config[2]: {frames} streams of {size}x{size} frames + {npts // 1000}k-pt clouds per step, one GPU, "
+                        "inputs resident in HBM", "robots_per_frame": [int(c) for c in counts][:4],
+            "rois_per_step": int(sum(counts)),
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                         "flops_per_step": st["conv_flops"], "conv_ms_per_step": conv_ms, "car_net_ms": car_ms / steps,
+                         "armor_net_ms": armor_ms / steps, "conv_share_of_step": conv_ms / (ms / steps)}}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -266,6 +316,7 @@ def run_ours(args, rank, world, local_rank):
         jobs.put((rec_array_t.from_buffer_copy(recs), n))
 
     conv_acc = [0.0, 0.0, 0]
+    step_stats = {}
 
     def step_resident(i):
         j = i % POOL
@@ -293,11 +344,13 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]   # step boundaries: median / p99 of a step
         conv_acc[:] = [0.0, 0.0, 0]          # per-step network replay times of the timed steps only
         e0.record(stream)
         n = 0
         for i in range(steps):
             n = fn(warmup + i)
+            marks[i].record(stream)
         if world > 1:
             jobs.join()                      # every step's exchange has been issued ...
         stream.wait_stream(comm_stream)      # ... and belongs to the timed region
@@ -308,6 +361,9 @@ def run_ours(args, rank, world, local_rank):
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        per = [e0.elapsed_time(marks[0])] + [marks[i - 1].elapsed_time(marks[i]) for i in range(1, steps)]
+        step_stats[fn.__name__] = {"median_ms": float(np.median(per)), "p99_ms": float(np.percentile(per, 99)),
+                                   "min_ms": float(np.min(per)), "max_ms": float(np.max(per))}
         return float(ms.item()), n
 
     warmup = max(args.warmup, 3)
@@ -367,6 +423,28 @@ def run_ours(args, rank, world, local_rank):
     peak_tf, peak_hbm, peak_src = peaks()
     achieved_tf = stats["conv_flops"] / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
 
+    # BASELINE config[2]: throughput mode, 16 streams of 1280x1280 frames + 100k-pt clouds per step on one GPU
+    throughput = None
+    if world == 1 and not args.no_throughput:
+        try:
+            throughput = throughput_leg(torch, rr, fx, dev, local_rank, stream, loc_stream, bg, cloud, peaks()[0])
+        except Exception as e:   # noqa: BLE001
+            throughput = {"value": None, "error": str(e)[:300]}
+    # TensorRT stand-in on the same GPU: the two ONNX graphs through torch + cuDNN fp16 channels-last
+    library = None
+    if world == 1 and not args.no_library_baseline and fx.have_onnx():
+        try:
+            torch.cuda.set_stream(torch.cuda.default_stream(dev))
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import library_baseline
+            library = library_baseline.measure(os.path.join(ROOT, "rm_radar_b200", "engines"), max(k_cars, 1), 20, local_rank)
+            library["note"] = ("NOT the reference arm: a same-GPU library baseline for the conv stacks only (the reference runs them "
+                               "through TensorRT FP16, detector.h:122); compare conv_stack_ms_graph with roofline.conv_ms_per_step")
+        except Exception as e:   # noqa: BLE001
+            library = {"error": str(e)[:300]}
+        finally:
+            torch.cuda.set_stream(stream)
+
     if world > 1:
         jobs.put(None)                       # stop the publisher thread
     if rank != 0:
@@ -398,7 +476,13 @@ def run_ours(args, rank, world, local_rank):
                      "conv_share_of_step": conv_ms / (ms_res / args.steps),
                      "frac_of_conv_bound_frames_per_s": (value / world) / (peak_tf * 1e12 / stats["conv_flops"])},
         "robots_per_frame": n_robots,
+        "latency": {"value_leg": step_stats.get("step_resident"), "e2e_leg": step_stats.get("step_e2e"),
+                    "how": "CUDA events between consecutive steps on the detector stream (one step = one rmr_run_once call)"},
     }
+    if throughput is not None:
+        line["throughput"] = throughput
+    if library is not None:
+        line["library_baseline"] = library
     if jpeg_leg is not None:
         line["e2e_jpeg"] = jpeg_leg
     if world == 1 and not args.no_cpu_baseline:
@@ -420,6 +504,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-throughput", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

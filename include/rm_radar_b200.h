@@ -28,7 +28,10 @@ typedef enum rmr_status {
     RMR_OK = 0,
     RMR_ERR_INVALID_ARGUMENT = -1, /* std::invalid_argument in the reference ctors (detector.cpp:80,181) */
     RMR_ERR_RUNTIME = -2,          /* std::runtime_error (common.h:31-39, detector.cpp:184,199,205) */
-    RMR_ERR_CUDA = -3              /* CUDA_CHECK / CUDA_CHECK_NOEXCEPT failures (common.h:31-62) */
+    RMR_ERR_CUDA = -3,             /* CUDA_CHECK / CUDA_CHECK_NOEXCEPT failures (common.h:31-62) */
+    RMR_ERR_CAPACITY = -4          /* a fixed internal capacity was exceeded (candidates / detections per image, armours per
+                                      robot, foreground points, clusters): the reference has no such caps and returns every
+                                      survivor (detector.cu:561-579), so the call fails instead of returning a truncated result */
 } rmr_status;
 
 /* radar::Detection — src/detect/detection.h:25-68 (six floats, standard layout) */
@@ -100,6 +103,18 @@ int rmr_robot_detector_create(rmr_robot_detector_t** out, const char* car_engine
                               float iou_thresh, float car_nms_thresh, float car_conf_thresh,
                               float armor_nms_thresh, float armor_conf_thresh, int input_width, int input_height,
                               int compat, int device);
+/* throughput mode (BASELINE config[2]): the same detector for `frames` images per call — the car network runs them as
+ * one batch (Detector::detect(container of cv::Mat), detector.cu:439-502), the armor network every ROI of all of them */
+int rmr_robot_detector_create_batched(rmr_robot_detector_t** out, const char* car_engine, const char* armor_engine,
+                                      int image_width, int image_height, int armor_classes, int max_cars,
+                                      float iou_thresh, float car_nms_thresh, float car_conf_thresh,
+                                      float armor_nms_thresh, float armor_conf_thresh, int input_width,
+                                      int input_height, int compat, int device, int frames);
+/* frames: n_frames images of one size back to back (frame i at frames + i * height * stride_bytes), host or device;
+ * out is [n_frames][capacity], counts is [n_frames] */
+int rmr_robot_detector_detect_frames(rmr_robot_detector_t* d, const void* frames, int frames_on_device, int n_frames,
+                                     int width, int height, int stride_bytes, rmr_robot_t* out, int capacity,
+                                     int* counts);
 void rmr_robot_detector_destroy(rmr_robot_detector_t* d);
 /* RobotDetector::detect(const cv::Mat&) -> std::vector<Robot>   (detector.cpp:413-455) */
 int rmr_robot_detector_detect(rmr_robot_detector_t* d, const uint8_t* bgr, int width, int height, int stride_bytes,
@@ -231,6 +246,15 @@ int rmr_conv_selftest(int n, int h_in, int w_in, int cin, int cout, int k, int s
  * (slot map in csrc/conv.cu); `out` holds capacity_ctas * 64 int64 */
 int rmr_conv_timeline(int n, int h_in, int w_in, int cin, int cout, int k, int stride, long long* out,
                       int capacity_ctas, int* n_ctas);
+
+/* SampleRadar::runOnce for n_frames camera + LiDAR streams at once (throughput mode): locators[i] is the Locator of
+ * stream i (its own background / depth queue), frames and clouds are back to back (cloud i at
+ * xyz + i * n_points * point_stride_bytes).  The car network runs all frames as one batch while the locators update
+ * and cluster, the armor network all ROIs, then every locator searches its frame's robots.
+ * out is [n_frames][capacity], counts is [n_frames]. */
+int rmr_run_batch(rmr_robot_detector_t* d, rmr_locator_t* const* locators, int n_frames, const void* frames,
+                  int frames_on_device, int width, int height, int stride_bytes, const void* xyz, int clouds_on_device,
+                  int n_points, int point_stride_bytes, rmr_robot_t* out, int capacity, int* counts);
 
 /* planning aid (tests/tools only, no GPU needed): the launch plan the tcgen05 conv would use for one layer.
  * out[16] = version (1 = conv.cu, 2 = conv2.cu), block_n, splits, halo, m_tiles, ctas, tiles per CTA,

@@ -17,7 +17,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import RadarError  # noqa: F401
+from ._lib import CapacityError, RadarError  # noqa: F401
 
 __all__ = ["Detector", "RobotDetector", "Locator", "Robot", "Detection", "Label", "RadarError",
            "engine_path_for", "run_once", "run_once_records"]
@@ -233,16 +233,19 @@ class RobotDetector:
     def __init__(self, car_path, armor_path, image_size, armor_classes, max_cars, opt_cars, iou_thresh=0.75,
                  car_nms_thresh=0.65, car_conf_thresh=0.25, armor_nms_thresh=0.65, armor_conf_thresh=0.50,
                  input_width=640, input_height=640, input_name="images", input_channels=3, opt_level=5, *,
-                 compat=True, device=0):
+                 compat=True, device=0, frames=1):
+        """frames > 1: throughput mode (BASELINE config[2]) — detect_frames / run_batch take that many images per call."""
         self._lib = _lib.load()
         self._h = C.c_void_p()
         w, h = image_size
         car = engine_path_for(os.fspath(car_path))
         armor = engine_path_for(os.fspath(armor_path))
-        _lib.check(self._lib.rmr_robot_detector_create(
+        _lib.check(self._lib.rmr_robot_detector_create_batched(
             C.byref(self._h), car.encode(), armor.encode(), w, h, armor_classes, max_cars, iou_thresh,
             car_nms_thresh, car_conf_thresh, armor_nms_thresh, armor_conf_thresh, input_width, input_height,
-            int(compat), device))
+            int(compat), device, frames))
+        self.frames = frames
+        self._frame_recs = (_lib.RobotRec * (max_cars * frames))() if frames > 1 else None
         self.max_cars = max_cars
         self.armor_classes = armor_classes
         self.input_size = (input_width, input_height)
@@ -260,6 +263,16 @@ class RobotDetector:
         _lib.check(self._lib.rmr_robot_detector_detect(self._h, img.ctypes.data, img.shape[1], img.shape[0],
                                                        img.strides[0], self._recs, self.max_cars, C.byref(n)))
         return [_robot_from_rec(self._recs[i]) for i in range(min(n.value, self.max_cars))]
+
+    def detect_frames(self, images) -> list:
+        """RobotDetector::detect on each of n same-sized frames, the networks batched over them -> list of list[Robot]."""
+        batch = np.ascontiguousarray(np.stack([_as_bgr(im) for im in images]))
+        n, h, w = batch.shape[:3]
+        counts = (C.c_int * n)()
+        recs = self._frame_recs if self._frame_recs is not None else (_lib.RobotRec * (self.max_cars * n))()
+        _lib.check(self._lib.rmr_robot_detector_detect_frames(self._h, batch.ctypes.data, 0, n, w, h, w * 3, recs,
+                                                              self.max_cars, counts))
+        return [[_robot_from_rec(recs[f * self.max_cars + i]) for i in range(min(counts[f], self.max_cars))] for f in range(n)]
 
     def detect_jpeg(self, decoder: "JpegDecoder", file_bytes: bytes) -> list:
         """cv::imread + RobotDetector::detect (samples/main.cpp:24-40, detector.cpp:413-455): the JPEG is decoded on the
@@ -417,6 +430,27 @@ def run_once_records(detector: "RobotDetector", locator: "Locator", frame_ptr: i
                                           height, stride, C.c_void_p(cloud_ptr), int(cloud_on_device), n_points,
                                           point_stride, detector._recs, detector.max_cars, C.byref(n)))
     return detector._recs, min(n.value, detector.max_cars)
+
+
+def run_batch_records(detector: "RobotDetector", locators, frames_ptr: int, frames_on_device: bool, n_frames: int, width: int,
+                      height: int, stride: int, clouds_ptr: int, clouds_on_device: bool, n_points: int, point_stride: int):
+    """n camera + LiDAR streams at once (throughput mode, rmr_run_batch): returns (RobotRec array [n][max_cars], counts)."""
+    counts = (C.c_int * n_frames)()
+    handles = (C.c_void_p * n_frames)(*[loc._h for loc in locators])
+    _lib.check(detector._lib.rmr_run_batch(detector._h, handles, n_frames, C.c_void_p(frames_ptr), int(frames_on_device), width,
+                                           height, stride, C.c_void_p(clouds_ptr), int(clouds_on_device), n_points,
+                                           point_stride, detector._frame_recs, detector.max_cars, counts))
+    return detector._frame_recs, counts
+
+
+def run_batch(detector: "RobotDetector", locators, images, clouds) -> list:
+    """run_once for n streams at once on host arrays -> list of list[Robot] (frame i with locators[i])."""
+    batch = np.ascontiguousarray(np.stack([_as_bgr(im) for im in images]))
+    pts = np.ascontiguousarray(np.stack([np.asarray(c, np.float32)[:, :3] for c in clouds]))
+    n, h, w = batch.shape[:3]
+    recs, counts = run_batch_records(detector, locators, batch.ctypes.data, False, n, w, h, w * 3, pts.ctypes.data, False,
+                                     pts.shape[1], 12)
+    return [[_robot_from_rec(recs[f * detector.max_cars + i]) for i in range(min(counts[f], detector.max_cars))] for f in range(n)]
 
 
 def run_once(detector: "RobotDetector", locator: "Locator", image: np.ndarray, cloud, tracker: "Tracker | None" = None,

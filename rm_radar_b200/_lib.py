@@ -37,7 +37,7 @@ SYMBOLS = [
     "rmr_detector_create", "rmr_detector_destroy", "rmr_detector_detect", "rmr_detector_detect_batch",
     "rmr_detector_last_input", "rmr_detector_last_output", "rmr_detector_info", "rmr_detector_set_stream",
     "rmr_detector_time_forward", "rmr_detector_profile_ops", "rmr_detector_plan_stats",
-    "rmr_robot_detector_create", "rmr_robot_detector_destroy", "rmr_robot_detector_detect",
+    "rmr_robot_detector_create", "rmr_robot_detector_create_batched", "rmr_robot_detector_detect_frames", "rmr_run_batch", "rmr_robot_detector_destroy", "rmr_robot_detector_detect",
     "rmr_robot_detector_detect_device", "rmr_robot_detector_last_cars", "rmr_robot_detector_last_armors",
     "rmr_robot_detector_set_stream", "rmr_robot_detector_last_stats", "rmr_robot_detector_last_timing", "rmr_robot_detector_car",
     "rmr_robot_detector_armor",
@@ -55,6 +55,10 @@ _lib = None
 
 class RadarError(RuntimeError):
     pass
+
+
+class CapacityError(RadarError):
+    """RMR_ERR_CAPACITY: a fixed internal capacity was exceeded; the call fails instead of returning a truncated result."""
 
 
 def load():
@@ -84,6 +88,10 @@ def load():
     lib.rmr_detector_profile_ops.argtypes = [vp, ci, ci, P(cd), ci, P(ci)]
     lib.rmr_robot_detector_create.argtypes = [P(vp), C.c_char_p, C.c_char_p, ci, ci, ci, ci, cf, cf, cf, cf, cf,
                                               ci, ci, ci, ci]
+    lib.rmr_robot_detector_create_batched.argtypes = [P(vp), C.c_char_p, C.c_char_p, ci, ci, ci, ci, cf, cf, cf, cf, cf,
+                                                      ci, ci, ci, ci, ci]
+    lib.rmr_robot_detector_detect_frames.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, ci, P(ci)]
+    lib.rmr_run_batch.argtypes = [vp, P(vp), ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, vp, ci, P(ci)]
     lib.rmr_robot_detector_destroy.argtypes = [vp]
     lib.rmr_robot_detector_destroy.restype = None
     lib.rmr_robot_detector_detect.argtypes = [vp, vp, ci, ci, ci, P(RobotRec), ci, P(ci)]
@@ -145,4 +153,6 @@ def check(status: int):
     msg = load().rmr_last_error().decode(errors="replace")
     if status == -1:
         raise ValueError(msg)
+    if status == -4:
+        raise CapacityError(msg)
     raise RadarError(f"rm_radar_b200 status {status}: {msg}")

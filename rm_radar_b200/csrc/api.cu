@@ -50,6 +50,9 @@ int guarded(F&& f) {
     } catch (const CudaError& e) {
         g_last_error = e.what();
         return RMR_ERR_CUDA;
+    } catch (const CapacityError& e) {
+        g_last_error = e.what();
+        return RMR_ERR_CAPACITY;
     } catch (const std::exception& e) {
         g_last_error = e.what();
         return RMR_ERR_RUNTIME;
@@ -63,7 +66,10 @@ void fill_robot(const RobotRecord& r, rmr_robot_t* o) {
     o->is_detected = r.detected;
     o->label = r.detected ? r.label : -1;
     o->confidence = r.confidence;
-    o->n_armors = std::min<int>(static_cast<int>(r.armors.size()), RMR_MAX_ARMORS);
+    if (static_cast<int>(r.armors.size()) > RMR_MAX_ARMORS)
+        throw CapacityError("a robot carries " + std::to_string(r.armors.size()) + " armour detections, rmr_robot_t holds " +
+                            std::to_string(RMR_MAX_ARMORS));
+    o->n_armors = static_cast<int>(r.armors.size());
     for (int i = 0; i < o->n_armors; ++i) std::memcpy(&o->armors[i], &r.armors[i], sizeof(rmr_detection_t));
     o->cluster = -2;
 }
@@ -199,6 +205,39 @@ int rmr_robot_detector_create(rmr_robot_detector_t** out, const char* car_engine
         h->car_view.impl = &h->impl->car();
         h->armor_view.impl = &h->impl->armor();
         *out = h.release();
+    });
+}
+
+int rmr_robot_detector_create_batched(rmr_robot_detector_t** out, const char* car_engine, const char* armor_engine,
+                                      int image_width, int image_height, int armor_classes, int max_cars, float iou_thresh,
+                                      float car_nms_thresh, float car_conf_thresh, float armor_nms_thresh,
+                                      float armor_conf_thresh, int input_width, int input_height, int compat, int device,
+                                      int frames) {
+    return guarded([&] {
+        if (!out || !car_engine || !armor_engine) throw std::invalid_argument("null argument");
+        auto h = std::make_unique<rmr_robot_detector>();
+        h->impl = std::make_unique<RobotDetector>(car_engine, armor_engine, image_width, image_height, armor_classes,
+                                                  max_cars, iou_thresh, car_nms_thresh, car_conf_thresh,
+                                                  armor_nms_thresh, armor_conf_thresh, input_width, input_height,
+                                                  compat != 0, device, frames);
+        h->car_view.impl = &h->impl->car();
+        h->armor_view.impl = &h->impl->armor();
+        *out = h.release();
+    });
+}
+
+int rmr_robot_detector_detect_frames(rmr_robot_detector_t* d, const void* frames, int frames_on_device, int n_frames,
+                                     int width, int height, int stride_bytes, rmr_robot_t* out, int capacity,
+                                     int* counts) {
+    return guarded([&] {
+        if (!d || !out || !counts) throw std::invalid_argument("null argument");
+        d->impl->begin_batch(static_cast<const uint8_t*>(frames), frames_on_device != 0, n_frames, width, height, stride_bytes);
+        auto robots = d->impl->finish_batch();
+        for (int f = 0; f < n_frames; ++f) {
+            counts[f] = static_cast<int>(robots[f].size());
+            const int n = std::min<int>(counts[f], capacity);
+            for (int i = 0; i < n; ++i) fill_robot(robots[f][i], out + static_cast<size_t>(f) * capacity + i);
+        }
     });
 }
 
@@ -594,6 +633,61 @@ int rmr_run_once(rmr_robot_detector_t* d, rmr_locator_t* l, const void* frame, i
             }
         } else {
             RMR_CUDA(cudaStreamSynchronize(l->stream));
+        }
+    });
+}
+
+// ---------------------------------------------------------------- n frames at once (throughput mode)
+int rmr_run_batch(rmr_robot_detector_t* d, rmr_locator_t* const* locators, int n_frames, const void* frames,
+                  int frames_on_device, int width, int height, int stride_bytes, const void* xyz, int clouds_on_device,
+                  int n_points, int point_stride_bytes, rmr_robot_t* out, int capacity, int* counts) {
+    return guarded([&] {
+        if (!d || !locators || !out || !counts || n_frames <= 0) throw std::invalid_argument("null argument");
+        if (xyz && (point_stride_bytes % 4 != 0 || point_stride_bytes < 12)) throw std::invalid_argument("bad point stride");
+        for (int f = 0; f < n_frames; ++f)
+            if (!locators[f]) throw std::invalid_argument("null locator");
+        // 1. the car stage of every frame goes out first, nothing waits
+        d->impl->begin_batch(static_cast<const uint8_t*>(frames), frames_on_device != 0, n_frames, width, height, stride_bytes);
+        // 2. every stream's locator updates and clusters while the car network runs
+        const size_t cloud_floats = static_cast<size_t>(n_points) * (point_stride_bytes / 4);
+        for (int f = 0; f < n_frames; ++f) {
+            rmr_locator_t* l = locators[f];
+            RMR_CUDA(cudaSetDevice(l->device));
+            const float* cloud = static_cast<const float*>(xyz) + f * cloud_floats;
+            if (clouds_on_device) l->impl->update_device(cloud, n_points, point_stride_bytes / 4, l->stream);
+            else l->impl->update_host(cloud, n_points, point_stride_bytes / 4, l->stream);
+            l->impl->cluster(l->stream);
+        }
+        // 3. car results -> armor stage over all ROIs -> robots per frame
+        auto robots = d->impl->finish_batch();
+        // 4. Locator::search per stream: all launches first, then the waits
+        std::vector<std::vector<RectF>> rects(n_frames);
+        for (int f = 0; f < n_frames; ++f) {
+            counts[f] = static_cast<int>(robots[f].size());
+            const int n = std::min<int>(counts[f], capacity);
+            rmr_robot_t* o = out + static_cast<size_t>(f) * capacity;
+            rects[f].resize(n);
+            for (int i = 0; i < n; ++i) {
+                fill_robot(robots[f][i], o + i);
+                rects[f][i] = RectF{o[i].rect[0], o[i].rect[1], o[i].rect[2], o[i].rect[3], o[i].has_rect};
+            }
+            if (n > 0) locators[f]->impl->search_begin(rects[f].data(), n, locators[f]->stream);
+        }
+        std::vector<LocResult> res;
+        for (int f = 0; f < n_frames; ++f) {
+            const int n = static_cast<int>(rects[f].size());
+            rmr_locator_t* l = locators[f];
+            if (n == 0) { RMR_CUDA(cudaStreamSynchronize(l->stream)); continue; }
+            res.resize(n);
+            l->impl->search_end(res.data(), n, l->stream);
+            rmr_robot_t* o = out + static_cast<size_t>(f) * capacity;
+            for (int i = 0; i < n; ++i) {
+                if (!res[i].located) continue;
+                o[i].is_located = 1;
+                o[i].location[0] = res[i].x; o[i].location[1] = res[i].y; o[i].location[2] = res[i].z;
+                o[i].cluster = res[i].cluster;
+                o[i].cluster_points = res[i].npoints;
+            }
         }
     });
 }

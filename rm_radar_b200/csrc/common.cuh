@@ -17,6 +17,13 @@ struct CudaError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
+// A fixed internal capacity was exceeded (candidates per image, detections per image, armours per robot,
+// foreground points, clusters).  The reference has no such caps (it returns every survivor,
+// /root/reference/src/detect/detector.cu:561-579), so silently truncating would change results: the call fails instead.
+struct CapacityError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
 inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
     if (e != cudaSuccess) {
         throw CudaError(std::string(file) + ":" + std::to_string(line) + " " + what + ": " +

@@ -9,7 +9,8 @@ namespace rmr {
 
 namespace {
 
-constexpr int kMaxOut = 256;   // detections returned per image (the reference returns every survivor)
+constexpr int kHeadOut = 64;     // detections per image copied with the counts; longer lists take a second copy
+constexpr int kMaxOut = 1024;   // detections returned per image (the reference returns every survivor); more is a CapacityError
 
 // NHWC4 fp16 -> planar float (test inspection: the blobKernel layout, detector.cu:151-171)
 __global__ void input_to_planar_kernel(const __half* in, float* out, int hw, int n) {
@@ -88,6 +89,7 @@ Detector::Detector(const std::string& engine_path, int classes, int image_w, int
     RMR_CUDA(cudaMallocHost(&pinned_geoms_, sizeof(LetterboxGeom) * max_batch));
     RMR_CUDA(cudaMallocHost(&pinned_out_, sizeof(Detection) * kMaxOut * max_batch));
     RMR_CUDA(cudaMallocHost(&pinned_counts_, sizeof(int) * max_batch));
+    RMR_CUDA(cudaMallocHost(&pinned_cand_counts_, sizeof(int) * max_batch));
     RMR_CUDA(cudaEventCreate(&ev_fwd0_));
     RMR_CUDA(cudaEventCreate(&ev_fwd1_));
     frame_buffer(static_cast<size_t>(image_w) * image_h * 3);
@@ -101,7 +103,7 @@ Detector::~Detector() {
     if (ev_fwd0_) cudaEventDestroy(ev_fwd0_);
     if (ev_fwd1_) cudaEventDestroy(ev_fwd1_);
     cudaFree(staging_); cudaFree(dev_geoms_); cudaFree(dev_frame_);
-    cudaFreeHost(pinned_geoms_); cudaFreeHost(pinned_out_); cudaFreeHost(pinned_counts_); cudaFreeHost(pinned_frame_);
+    cudaFreeHost(pinned_geoms_); cudaFreeHost(pinned_out_); cudaFreeHost(pinned_counts_); cudaFreeHost(pinned_cand_counts_); cudaFreeHost(pinned_frame_);
     net_.reset();
     if (own_stream_) cudaStreamDestroy(own_stream_);
 }
@@ -146,7 +148,10 @@ void Detector::enqueue(const uint8_t* dev_frame, int stride, const Roi* rois, in
     RMR_CUDA(cudaEventRecord(ev_fwd1_, stream_));
     launch_postprocess(net_->levels(), classes_, n, dev_geoms_, conf_thresh_, nms_thresh_, post_, stream_);
     RMR_CUDA(cudaMemcpyAsync(pinned_counts_, post_.out_count, sizeof(int) * n, cudaMemcpyDeviceToHost, stream_));
-    RMR_CUDA(cudaMemcpyAsync(pinned_out_, post_.out, sizeof(Detection) * kMaxOut * n, cudaMemcpyDeviceToHost, stream_));
+    RMR_CUDA(cudaMemcpyAsync(pinned_cand_counts_, post_.cand_count, sizeof(int) * n, cudaMemcpyDeviceToHost, stream_));
+    // survivors are few: copy a compact head of every image's list now, the rest only if an image has more
+    RMR_CUDA(cudaMemcpy2DAsync(pinned_out_, sizeof(Detection) * kMaxOut, post_.out, sizeof(Detection) * kMaxOut,
+                               sizeof(Detection) * kHeadOut, n, cudaMemcpyDeviceToHost, stream_));
     int net_launches = 0;
     net_->plan_stats(n, &net_launches, nullptr, nullptr);
     last_launches_ = (any_clean ? 1 : 0) + (any_unclean ? 2 : 0) + net_launches + 2;
@@ -161,6 +166,21 @@ std::vector<std::vector<Detection>> Detector::collect() {
     RMR_CUDA(cudaSetDevice(device_));
     RMR_CUDA(cudaStreamSynchronize(stream_));
     RMR_CUDA(cudaEventElapsedTime(&last_forward_ms_, ev_fwd0_, ev_fwd1_));
+    int longest = 0;
+    for (int i = 0; i < n; ++i) {
+        // the reference returns every survivor; a truncated list would be a different result, so it is an error
+        if (pinned_cand_counts_[i] > kMaxCandidates)
+            throw CapacityError("image " + std::to_string(i) + ": " + std::to_string(pinned_cand_counts_[i]) +
+                                " anchors pass the confidence threshold, capacity " + std::to_string(kMaxCandidates));
+        if (pinned_counts_[i] > kMaxOut)
+            throw CapacityError("image " + std::to_string(i) + ": " + std::to_string(pinned_counts_[i]) +
+                                " detections survive NMS, capacity " + std::to_string(kMaxOut));
+        longest = std::max(longest, pinned_counts_[i]);
+    }
+    if (longest > kHeadOut) {
+        RMR_CUDA(cudaMemcpyAsync(pinned_out_, post_.out, sizeof(Detection) * kMaxOut * n, cudaMemcpyDeviceToHost, stream_));
+        RMR_CUDA(cudaStreamSynchronize(stream_));
+    }
     for (int i = 0; i < n; ++i) {
         const int c = std::min(pinned_counts_[i], kMaxOut);
         results[i].assign(pinned_out_ + static_cast<size_t>(i) * kMaxOut, pinned_out_ + static_cast<size_t>(i) * kMaxOut + c);
@@ -302,11 +322,14 @@ RobotRecord set_detection(const Detection& car, const std::vector<Detection>& ar
 RobotDetector::RobotDetector(const std::string& car_engine, const std::string& armor_engine, int image_w,
                              int image_h, int armor_classes, int max_cars, float iou_thresh, float car_nms,
                              float car_conf, float armor_nms, float armor_conf, int input_w, int input_h, bool compat,
-                             int device)
-    : max_cars_(max_cars), iou_thresh_(iou_thresh) {
-    // detector.cpp:377-404: car detector batch 1 / 1 class, armor detector batch max_cars
-    car_ = std::make_unique<Detector>(car_engine, 1, image_w, image_h, 1, car_nms, car_conf, input_w, input_h, compat, device);
-    armor_ = std::make_unique<Detector>(armor_engine, armor_classes, image_w, image_h, max_cars, armor_nms, armor_conf,
+                             int device, int frames)
+    : max_cars_(max_cars), iou_thresh_(iou_thresh), frames_(frames) {
+    if (frames < 1 || frames > 64) throw std::invalid_argument("frames must be in [1, 64]");
+    // detector.cpp:377-404: car detector batch 1 / 1 class, armor detector batch max_cars.  Throughput mode: `frames`
+    // images per car-network call; the armor network takes the ROIs of all of them in chunks of its batch size
+    car_ = std::make_unique<Detector>(car_engine, 1, image_w, image_h * frames, frames, car_nms, car_conf, input_w, input_h, compat, device);
+    const int armor_batch = frames == 1 ? max_cars : std::min(max_cars * frames, std::max(max_cars, 128));
+    armor_ = std::make_unique<Detector>(armor_engine, armor_classes, image_w, image_h * frames, armor_batch, armor_nms, armor_conf,
                                         input_w, input_h, compat, device);
     armor_->set_stream(car_->stream());
 }
@@ -377,12 +400,19 @@ std::vector<RobotRecord> RobotDetector::finish() {
     }
     last_cars_ = cars;
     last_armors_.assign(cars.size(), {});
+    for (size_t i = 0; i < cars.size(); ++i)
+        if (roi_of_car[i] >= 0) last_armors_[i] = armor_batch[roi_of_car[i]];
+    return assemble(cars, last_armors_);
+}
+
+// Robot::setDetection per car, then the label de-duplication of RobotDetector::detect (detector.cpp:426-455)
+std::vector<RobotRecord> RobotDetector::assemble(const std::vector<Detection>& cars,
+                                                 const std::vector<std::vector<Detection>>& armors) {
     std::vector<RobotRecord> robots;
     robots.reserve(cars.size());
     std::map<int, RobotRecord> by_label;
     for (size_t i = 0; i < cars.size(); ++i) {
-        if (roi_of_car[i] >= 0) last_armors_[i] = armor_batch[roi_of_car[i]];
-        RobotRecord robot = set_detection(cars[i], last_armors_[i]);
+        RobotRecord robot = set_detection(cars[i], armors[i]);
         if (!robot.detected) {
             robots.push_back(robot);
             continue;
@@ -400,6 +430,69 @@ std::vector<RobotRecord> RobotDetector::finish() {
     }
     for (auto& kv : by_label) robots.push_back(kv.second);
     return robots;
+}
+
+// ---- throughput mode: `n` frames per call ------------------------------------------------------------------
+void RobotDetector::begin_batch(const uint8_t* frames, bool on_device, int n, int w, int h, int stride) {
+    if (!frames || n <= 0 || w <= 0 || h <= 0 || stride < w * 3) throw std::invalid_argument("bad image batch");
+    if (n > frames_) throw std::invalid_argument("more frames than the detector was created for");
+    RMR_CUDA(cudaSetDevice(car_->device()));
+    const uint8_t* dev = frames;
+    if (!on_device) {
+        const size_t bytes = static_cast<size_t>(stride) * h * n;
+        uint8_t* buf = car_->frame_buffer(bytes);
+        RMR_CUDA(cudaMemcpyAsync(buf, frames, bytes, cudaMemcpyHostToDevice, car_->stream()));
+        dev = buf;
+    }
+    cur_frame_ = dev; cur_w_ = w; cur_h_ = h; cur_stride_ = stride; cur_n_ = n;
+    std::vector<Roi> full(n);
+    for (int i = 0; i < n; ++i) full[i] = Roi{0, i * h, w, h};   // the batch is one tall strip of rows
+    car_->enqueue(dev, stride, full.data(), n);
+}
+
+std::vector<std::vector<RobotRecord>> RobotDetector::finish_batch() {
+    if (cur_frame_ == nullptr) throw std::invalid_argument("RobotDetector::finish_batch without begin_batch");
+    const uint8_t* dev = cur_frame_;
+    const int n = cur_n_, h = cur_h_, stride = cur_stride_;
+    cur_frame_ = nullptr;
+    std::vector<std::vector<Detection>> cars = car_->collect();
+    last_launches_ = car_->last_launches();
+    last_flops_ = car_->net().flops_per_image() * n;
+    last_car_ms_ = car_->last_forward_ms();
+    last_armor_ms_ = 0.f;
+    // ROIs of every frame, in frame order; (frame, car) of each ROI
+    std::vector<Roi> rois;
+    std::vector<std::vector<int>> roi_of_car(n);
+    for (int f = 0; f < n; ++f) {
+        if (static_cast<int>(cars[f].size()) > max_cars_) cars[f].resize(max_cars_);
+        roi_of_car[f].assign(cars[f].size(), -1);
+        for (size_t i = 0; i < cars[f].size(); ++i) {
+            const Detection& c = cars[f][i];
+            Roi r{static_cast<int>(c.x), static_cast<int>(c.y) + f * h, static_cast<int>(c.width), static_cast<int>(c.height)};
+            if (r.w <= 0 || r.h <= 0) continue;
+            roi_of_car[f][i] = static_cast<int>(rois.size());
+            rois.push_back(r);
+        }
+    }
+    std::vector<std::vector<Detection>> armor_all(rois.size());
+    const int chunk = armor_->max_batch();
+    for (size_t r0 = 0; r0 < rois.size(); r0 += chunk) {
+        const int m = static_cast<int>(std::min<size_t>(chunk, rois.size() - r0));
+        auto part = armor_->detect_device_rois(dev, stride, rois.data() + r0, m);
+        for (int i = 0; i < m; ++i) armor_all[r0 + i] = std::move(part[i]);
+        last_launches_ += armor_->last_launches();
+        last_armor_ms_ += armor_->last_forward_ms();
+        last_flops_ += armor_->net().flops_per_image() * m;
+    }
+    std::vector<std::vector<RobotRecord>> out(n);
+    for (int f = 0; f < n; ++f) {
+        std::vector<std::vector<Detection>> armors(cars[f].size());
+        for (size_t i = 0; i < cars[f].size(); ++i)
+            if (roi_of_car[f][i] >= 0) armors[i] = armor_all[roi_of_car[f][i]];
+        out[f] = assemble(cars[f], armors);
+        if (f == n - 1) { last_cars_ = cars[f]; last_armors_ = armors; }
+    }
+    return out;
 }
 
 }  // namespace rmr

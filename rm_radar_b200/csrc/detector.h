@@ -64,6 +64,7 @@ private:
     LetterboxGeom *dev_geoms_ = nullptr, *pinned_geoms_ = nullptr;
     Detection* pinned_out_ = nullptr;
     int* pinned_counts_ = nullptr;
+    int* pinned_cand_counts_ = nullptr;    // candidates per image before NMS (capacity check)
     int last_launches_ = 0;
     cudaEvent_t ev_fwd0_ = nullptr, ev_fwd1_ = nullptr;
     float last_forward_ms_ = 0.f;
@@ -79,9 +80,16 @@ struct RobotRecord {
 
 class RobotDetector {
 public:
+    // frames > 1: throughput mode — the car network runs `frames` images per call and the armor network every
+    // ROI of those frames (Detector::detect(container), /root/reference/src/detect/detector.cu:439-502)
     RobotDetector(const std::string& car_engine, const std::string& armor_engine, int image_w, int image_h,
                   int armor_classes, int max_cars, float iou_thresh, float car_nms, float car_conf, float armor_nms,
-                  float armor_conf, int input_w, int input_h, bool compat, int device);
+                  float armor_conf, int input_w, int input_h, bool compat, int device, int frames = 1);
+    // frames of one size, back to back in memory (frame i at frame + i * h * stride); begin_batch enqueues the car
+    // stage for all of them and returns at once, finish_batch does the rest and returns the robots per frame
+    void begin_batch(const uint8_t* frames, bool on_device, int n, int w, int h, int stride);
+    std::vector<std::vector<RobotRecord>> finish_batch();
+    int frames() const { return frames_; }
     std::vector<RobotRecord> detect_host(const uint8_t* bgr, int w, int h, int stride);
     std::vector<RobotRecord> detect_device(const uint8_t* dev_bgr, int w, int h, int stride);
     // split form: begin() uploads / enqueues the car stage and returns at once, finish() does the rest
@@ -107,7 +115,9 @@ private:
     double last_flops_ = 0;
     float last_car_ms_ = 0.f, last_armor_ms_ = 0.f;
     const uint8_t* cur_frame_ = nullptr;
-    int cur_w_ = 0, cur_h_ = 0, cur_stride_ = 0;
+    int cur_w_ = 0, cur_h_ = 0, cur_stride_ = 0, cur_n_ = 0;
+    int frames_ = 1;
+    std::vector<RobotRecord> assemble(const std::vector<Detection>& cars, const std::vector<std::vector<Detection>>& armors);
 };
 
 }  // namespace rmr

@@ -533,6 +533,7 @@ Locator::Locator(const LocatorConfig& cfg, int max_points, int max_foreground, i
     RMR_CUDA(cudaMalloc(&cluster_id_, sizeof(int) * max_fg_));
     RMR_CUDA(cudaMalloc(&root_list_, sizeof(int) * (kMaxClusters + 1)));
     RMR_CUDA(cudaMalloc(&hist_, sizeof(int) * static_cast<size_t>(max_robots_) * (kMaxClusters + 1)));
+    RMR_CUDA(cudaMallocHost(&pinned_counters_, sizeof(int) * 4));
     RMR_CUDA(cudaMalloc(&dev_rects_, sizeof(RectF) * max_robots_));
     RMR_CUDA(cudaMalloc(&dev_results_, sizeof(LocResult) * max_robots_));
     RMR_CUDA(cudaMallocHost(&pinned_rects_, sizeof(RectF) * max_robots_));
@@ -546,7 +547,7 @@ Locator::~Locator() {
     cudaFree(ring_); cudaFree(label_img_); cudaFree(block_counts_); cudaFree(block_offsets_); cudaFree(counters_);
     cudaFree(fg_pts_); cudaFree(parent_); cudaFree(next_); cudaFree(heads_); cudaFree(cell_keys_); cudaFree(comp_size_);
     cudaFree(cluster_id_); cudaFree(root_list_); cudaFree(hist_); cudaFree(dev_rects_); cudaFree(dev_results_);
-    cudaFreeHost(pinned_rects_); cudaFreeHost(pinned_results_);
+    cudaFreeHost(pinned_rects_); cudaFreeHost(pinned_results_); cudaFreeHost(pinned_counters_);
 }
 
 // Appendix B#13: the reference never initialises its images and relies on fresh zero pages
@@ -633,12 +634,30 @@ void Locator::search_device(const RectF* dev_rects, LocResult* dev_results, int 
 
 void Locator::search(const RectF* rects, LocResult* results, int n, cudaStream_t s) {
     if (n <= 0) return;
+    search_begin(rects, n, s);
+    search_end(results, n, s);
+}
+
+// asynchronous half: rectangles up, search kernel, results + the counters of the last cluster() down
+void Locator::search_begin(const RectF* rects, int n, cudaStream_t s) {
+    if (n <= 0) return;
     if (n > max_robots_) throw std::invalid_argument("Locator::search: too many robots");
     std::memcpy(pinned_rects_, rects, sizeof(RectF) * n);
     RMR_CUDA(cudaMemcpyAsync(dev_rects_, pinned_rects_, sizeof(RectF) * n, cudaMemcpyHostToDevice, s));
     search_device(dev_rects_, dev_results_, n, s);
     RMR_CUDA(cudaMemcpyAsync(pinned_results_, dev_results_, sizeof(LocResult) * n, cudaMemcpyDeviceToHost, s));
+    RMR_CUDA(cudaMemcpyAsync(pinned_counters_, counters_, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+}
+
+void Locator::search_end(LocResult* results, int n, cudaStream_t s) {
+    if (n <= 0) return;
     RMR_CUDA(cudaStreamSynchronize(s));
+    // the reference clusters every foreground point (locate.cpp:237-263); a truncated foreground or cluster list would
+    // move robots, so running out of room is an error, not a smaller answer
+    if (pinned_counters_[3] > max_fg_)
+        throw CapacityError(std::to_string(pinned_counters_[3]) + " foreground pixels, Locator capacity " + std::to_string(max_fg_));
+    if (pinned_counters_[2] > kMaxClusters)
+        throw CapacityError(std::to_string(pinned_counters_[2]) + " clusters, Locator capacity " + std::to_string(kMaxClusters));
     std::memcpy(results, pinned_results_, sizeof(LocResult) * n);
 }
 

@@ -55,6 +55,9 @@ public:
     void cluster(cudaStream_t s);
     // Locator::search (locate.cpp:276-326); rects/results are host arrays of `n`
     void search(const RectF* rects, LocResult* results, int n, cudaStream_t s);
+    // the two halves of search(): everything enqueued / the one wait (several locators overlap their searches)
+    void search_begin(const RectF* rects, int n, cudaStream_t s);
+    void search_end(LocResult* results, int n, cudaStream_t s);
     void search_device(const RectF* dev_rects, LocResult* dev_results, int n, cudaStream_t s);
 
     int wz() const { return calib_.wz; }
@@ -95,6 +98,7 @@ private:
     LocResult* dev_results_ = nullptr;
     RectF* pinned_rects_ = nullptr;
     LocResult* pinned_results_ = nullptr;
+    int* pinned_counters_ = nullptr;       // counters of the last cluster(): [0] foreground kept, [1] clusters kept, [2] clusters found, [3] foreground found
 };
 
 constexpr int kMaxClusters = 8191;

@@ -11,7 +11,7 @@ struct Detection {
 };
 static_assert(sizeof(Detection) == 24, "Detection must stay a 6-float POD");
 
-constexpr int kMaxCandidates = 4096;   // per image, after the confidence threshold
+constexpr int kMaxCandidates = 16384;   // per image, after the confidence threshold; exceeding it is a CapacityError
 
 struct PostBuffers {
     // device

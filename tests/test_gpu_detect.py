@@ -192,6 +192,41 @@ def test_run_once_equals_separate_calls():
 
 
 @needs_models
+def test_run_batch_equals_run_once_per_stream():
+    """Throughput mode (BASELINE config[2], rmr_run_batch): n camera + LiDAR streams in one call — the car network batched over
+    the frames, the armor network over all their ROIs, one Locator per stream — gives every stream what rmr_run_once
+    gives it alone (Detector::detect(container) vs detect(Mat), /root/reference/src/detect/detector.cu:380-502)."""
+    clouds = fx.load_clouds()
+    frames = [fx.load_frame(0), fx.load_frame(5), np.ascontiguousarray(fx.load_frame(0)[:, ::-1])]
+    keys = ["c0", "c1", "c2"]
+    n = len(frames)
+    det1 = rr.RobotDetector(fx.engine("car"), fx.engine("armor"), fx.IMAGE_SIZE, fx.CLASS_NUM, fx.MAX_BATCH, fx.OPT_BATCH)
+    detn = rr.RobotDetector(fx.engine("car"), fx.engine("armor"), fx.IMAGE_SIZE, fx.CLASS_NUM, fx.MAX_BATCH, fx.OPT_BATCH, frames=n)
+    mk = lambda: rr.Locator(*fx.IMAGE_SIZE, fx.INTRINSIC, fx.LIDAR_TO_CAMERA, fx.WORLD_TO_CAMERA)   # noqa: E731
+    locs_a, locs_b = [mk() for _ in range(n)], [mk() for _ in range(n)]
+    for la, lb in zip(locs_a, locs_b):
+        la.update(clouds["background"]); lb.update(clouds["background"])
+    npts = min(len(clouds[k]) for k in keys)
+    cl = [np.ascontiguousarray(clouds[k][:npts]) for k in keys]
+    want = [rr.run_once(det1, locs_a[i], frames[i], cl[i]) for i in range(n)]
+    got = rr.run_batch(detn, locs_b, frames, cl)
+    assert len(got) == n and sum(len(w) for w in want) >= 6
+    for g_robots, w_robots in zip(got, want):
+        assert len(g_robots) == len(w_robots)
+        for g, w in zip(g_robots, w_robots):
+            assert g.label == w.label and (g.confidence is None) == (w.confidence is None)
+            if g.confidence is not None:
+                assert abs(g.confidence - w.confidence) <= 5e-3
+            assert fx.iou_xywh(g.rect, w.rect) >= 0.99
+            assert (g.location is None) == (w.location is None)
+            if g.location is not None:
+                assert np.allclose(g.location, w.location, atol=1e-3)
+    # detect_frames (detection only) agrees with the cascade inside run_batch
+    only = detn.detect_frames(frames)
+    assert [[(r.label, r.rect) for r in f] for f in only] == [[(r.label, r.rect) for r in f] for f in got]
+
+
+@needs_models
 def test_whole_chain_jpeg_detect_locate_track():
     """SampleRadar::runOnce end to end (sample_radar.h:106-127): JPEG in, tracked robots out, over repeated frames."""
     from oracle import track_oracle as to

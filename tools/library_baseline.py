@@ -58,8 +58,17 @@ class CudnnNet:
                 env[name] = val
         return env[self.out]
 
+    def _same_device(self, ins):
+        """constant-folded shape arithmetic stays on the host; an operand that meets a device tensor follows it"""
+        dev = [t for t in ins if isinstance(t, torch.Tensor) and t.is_cuda]
+        if not dev:
+            return ins
+        return [t.to(dev[0].device) if isinstance(t, torch.Tensor) and not t.is_cuda else t for t in ins]
+
     def _run(self, n, ins):
         op, a = n.op, n.attrs
+        if op in ("Mul", "Add", "Sub", "Div", "Concat"):
+            ins = self._same_device(ins)
         if op == "Conv":
             p = a["pads"]
             return F.conv2d(ins[0], ins[1], ins[2] if len(ins) > 2 else None, stride=a["strides"], padding=(p[0], p[1]),
