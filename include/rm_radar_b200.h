@@ -256,6 +256,12 @@ int rmr_run_batch(rmr_robot_detector_t* d, rmr_locator_t* const* locators, int n
                   int frames_on_device, int width, int height, int stride_bytes, const void* xyz, int clouds_on_device,
                   int n_points, int point_stride_bytes, rmr_robot_t* out, int capacity, int* counts);
 
+/* post-processing self-test (tests only): the NMS + restore kernel on caller-supplied candidates [n][6] =
+ * (x, y, w, h, label, conf) in network coordinates, row index = anchor index (NMSKernel + the NaN filter,
+ * detector.cu:315-360, 561-579).  Survivors come back in anchor order.  More candidates than the internal capacity:
+ * RMR_ERR_CAPACITY. */
+int rmr_postprocess_selftest(const float* candidates, int n, float nms_thresh, rmr_detection_t* out, int capacity, int* count);
+
 /* planning aid (tests/tools only, no GPU needed): the launch plan the tcgen05 conv would use for one layer.
  * out[16] = version (1 = conv.cu, 2 = conv2.cu), block_n, splits, halo, m_tiles, ctas, tiles per CTA,
  * k-blocks per tile and CTA, activation slots, weight slots, weights resident (0/1), shared memory bytes,

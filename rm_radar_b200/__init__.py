@@ -130,7 +130,7 @@ class Detector:
         self.classes = classes
         self.max_batch_size = max_batch_size
         self.input_size = (input_width, input_height)
-        self._cap = 256
+        self._cap = 1024   # kMaxOut of the library: every survivor comes back
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -206,7 +206,7 @@ class Detector:
 
 class _DetectorView(Detector):
     def __init__(self, lib, handle, classes, input_size):   # borrowed handle: never destroyed
-        self._lib, self._h, self.classes, self.input_size, self._cap = lib, C.c_void_p(handle), classes, input_size, 256
+        self._lib, self._h, self.classes, self.input_size, self._cap = lib, C.c_void_p(handle), classes, input_size, 1024
 
     def __del__(self):
         pass
@@ -623,6 +623,15 @@ def conv_selftest(n, h, w, cin, cout, k, stride, act=1, residual=0, out_f32=0, s
     _lib.check(lib.rmr_conv_selftest(n, h, w, cin, cout, k, stride, act, residual, out_f32, seed, iters,
                                      C.byref(d), C.byref(r), C.byref(ms)))
     return d.value, r.value, ms.value
+
+
+def postprocess_selftest(candidates: np.ndarray, nms_thresh: float) -> np.ndarray:
+    """NMS + restore kernel on caller-supplied candidates [n, 6] (tests only) -> surviving rows [m, 6] in anchor order."""
+    c = np.ascontiguousarray(candidates, np.float32).reshape(-1, 6)
+    out = np.zeros((max(len(c), 1), 6), np.float32)
+    n = C.c_int()
+    _lib.check(_lib.load().rmr_postprocess_selftest(c.ctypes.data, len(c), nms_thresh, out.ctypes.data, len(out), C.byref(n)))
+    return out[:min(n.value, len(out))]
 
 
 def conv_timeline(n, h, w, cin, cout, k, stride, max_ctas=4096):

@@ -836,6 +836,15 @@ int rmr_conv_timeline(int n, int h_in, int w_in, int cin, int cout, int k, int s
     });
 }
 
+int rmr_postprocess_selftest(const float* candidates, int n, float nms_thresh, rmr_detection_t* out, int capacity, int* count) {
+    return guarded([&] {
+        if ((!candidates && n > 0) || !out || !count) throw std::invalid_argument("null argument");
+        auto dets = postprocess_selftest(candidates, n, nms_thresh);
+        *count = static_cast<int>(dets.size());
+        std::memcpy(out, dets.data(), sizeof(rmr_detection_t) * std::min<int>(*count, capacity));
+    });
+}
+
 int rmr_conv_plan(int n, int h_in, int w_in, int cin, int cout, int k, int stride, int* out) {
     return guarded([&] {
         const int pad = k / 2;

@@ -1,5 +1,9 @@
 #include "postprocess.h"
 
+#include <algorithm>
+#include <cstring>
+#include <string>
+
 namespace rmr {
 
 namespace {
@@ -197,6 +201,46 @@ void launch_postprocess(const std::vector<HeadLevel>& levels, int num_classes, i
     nms_restore_kernel<<<batch, 256, 0, s>>>(pb.cand, pb.cand_count, sorted, dev_geoms, nms_thresh, pb.out,
                                              pb.out_count, pb.max_out);
     RMR_CUDA(cudaGetLastError());
+}
+
+std::vector<Detection> postprocess_selftest(const float* cand6, int n, float nms_thresh) {
+    if (n < 0) throw std::invalid_argument("negative candidate count");
+    if (n > kMaxCandidates)
+        throw CapacityError(std::to_string(n) + " anchors pass the confidence threshold, capacity " + std::to_string(kMaxCandidates));
+    constexpr int kOut = 4096;
+    PostBuffers pb;
+    post_alloc(pb, 1, kOut);
+    std::vector<float> h(static_cast<size_t>(std::max(n, 1)) * 8, 0.f);
+    for (int i = 0; i < n; ++i) {            // reversed arrival order, anchor = original row
+        float* o = h.data() + static_cast<size_t>(n - 1 - i) * 8;
+        for (int k = 0; k < 6; ++k) o[k] = cand6[i * 6 + k];
+        std::memcpy(o + 6, &i, sizeof(int));
+    }
+    LetterboxGeom g{};
+    g.ratio = 1.f; g.dw = 0.f; g.dh = 0.f; g.width = 1e9f; g.height = 1e9f;
+    LetterboxGeom* dg = nullptr;
+    std::vector<Detection> out;
+    try {
+        RMR_CUDA(cudaMalloc(&dg, sizeof(g)));
+        RMR_CUDA(cudaMemcpy(dg, &g, sizeof(g), cudaMemcpyHostToDevice));
+        RMR_CUDA(cudaMemcpy(pb.cand, h.data(), sizeof(float) * 8 * n, cudaMemcpyHostToDevice));
+        RMR_CUDA(cudaMemcpy(pb.cand_count, &n, sizeof(int), cudaMemcpyHostToDevice));
+        float* sorted = pb.cand + static_cast<size_t>(8) * kMaxCandidates * pb.max_batch;
+        nms_restore_kernel<<<1, 256>>>(pb.cand, pb.cand_count, sorted, dg, nms_thresh, pb.out, pb.out_count, pb.max_out);
+        RMR_CUDA(cudaGetLastError());
+        int cnt = 0;
+        RMR_CUDA(cudaMemcpy(&cnt, pb.out_count, sizeof(int), cudaMemcpyDeviceToHost));
+        if (cnt > kOut) throw CapacityError(std::to_string(cnt) + " detections survive NMS, self-test capacity " + std::to_string(kOut));
+        out.resize(cnt);
+        if (cnt) RMR_CUDA(cudaMemcpy(out.data(), pb.out, sizeof(Detection) * cnt, cudaMemcpyDeviceToHost));
+    } catch (...) {
+        cudaFree(dg);
+        post_free(pb);
+        throw;
+    }
+    cudaFree(dg);
+    post_free(pb);
+    return out;
 }
 
 }  // namespace rmr

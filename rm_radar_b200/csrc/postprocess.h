@@ -1,4 +1,6 @@
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 #include "net.h"
 #include "preprocess.h"
@@ -32,5 +34,10 @@ void post_free(PostBuffers& pb);
 void launch_postprocess(const std::vector<HeadLevel>& levels, int num_classes, int batch,
                         const LetterboxGeom* dev_geoms, float conf_thresh, float nms_thresh, PostBuffers& pb,
                         cudaStream_t s);
+
+// Test hook (tests only): nms_restore_kernel on caller-supplied candidates [n][6] = (x, y, w, h, label, conf) in
+// network coordinates, row index = anchor index, uploaded in reverse order (the kernel must restore anchor order);
+// identity un-letterboxing.  More than kMaxCandidates rows is a CapacityError, like in the product path.
+std::vector<Detection> postprocess_selftest(const float* cand6, int n, float nms_thresh);
 
 }  // namespace rmr

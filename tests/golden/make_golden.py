@@ -106,6 +106,53 @@ def main():
     np.savez_compressed(os.path.join(HERE, "expected.npz"), **out)
 
 
+def make_all_assets():
+    """expected_all.npz: the oracle on ALL ten frames and ten clouds of the reference (north_star: "the same
+    assets/images + assets/clouds inputs"); frame i is paired with cloud i, boxes = that frame's cars.  The eight extra
+    frames and the extra clouds are input data, copied by __graft_entry__.build() into the git-ignored
+    tests/golden/_assets/ (they travel to the GPU box with the snapshot); only the oracle's outputs are committed."""
+    import cv2
+    car = OnnxNet(f"{REF}/models/car.onnx")
+    armor = OnnxNet(f"{REF}/models/armor.onnx")
+    out = {}
+    bg = lo.read_pcd(f"{REF}/assets/clouds/background.pcd")[::4].copy()
+    for i in range(10):
+        img = cv2.imread(f"{REF}/assets/images/{i}.jpg", cv2.IMREAD_COLOR)
+        tr = do.CascadeTrace()
+        robots = do.robot_detect(img, lambda x: car(x).numpy(), lambda x: armor(x).numpy(), trace=tr)
+        out[f"f{i}_cars"] = tr.car_dets
+        out[f"f{i}_armor_counts"] = np.asarray([len(a) for a in tr.armor_dets], np.int32)
+        out[f"f{i}_armors"] = np.concatenate(tr.armor_dets) if tr.armor_dets else np.zeros((0, 6), np.float32)
+        out[f"f{i}_robot_labels"] = np.asarray([r.label for r in robots if r.is_detected()], np.int32)
+        out[f"f{i}_robot_conf"] = np.asarray([r.confidence for r in robots if r.is_detected()], np.float32)
+        out[f"f{i}_robot_rects"] = np.asarray([r.rect for r in robots], np.float32)
+        # locate: a fresh Locator per pair (background, then cloud i), boxes = the frame's robots in output order
+        cloud = lo.read_pcd(f"{REF}/assets/clouds/{i}.pcd")
+        loc = lo.LocatorOracle(fx.IMAGE_SIZE[0], fx.IMAGE_SIZE[1], fx.INTRINSIC, fx.LIDAR_TO_CAMERA, fx.WORLD_TO_CAMERA)
+        loc.update(bg); loc.update(cloud); loc.cluster()
+        res = loc.search([tuple(r.rect) for r in robots])
+        out[f"f{i}_located"] = np.asarray([r is not None for r in res])
+        out[f"f{i}_locations"] = np.asarray([r if r is not None else (np.nan,) * 3 for r in res], np.float64)
+        out[f"f{i}_fg_clusters"] = np.asarray([len(loc.fg_points), loc.num_clusters], np.int32)
+        print(i, "cars", len(tr.car_dets), "armors", out[f"f{i}_armor_counts"].tolist(), "labels", out[f"f{i}_robot_labels"].tolist(),
+              "located", int(out[f"f{i}_located"].sum()), "fg/clusters", out[f"f{i}_fg_clusters"].tolist(), flush=True)
+    np.savez_compressed(os.path.join(HERE, "expected_all.npz"), **out)
+
+
+def copy_assets(dst=None):
+    """Input data of the all-assets tests: frames 0-9 and clouds 0-9 + background (subsampled like clouds.npz)."""
+    dst = dst or os.path.join(HERE, "_assets")
+    os.makedirs(dst, exist_ok=True)
+    for i in range(10):
+        if not os.path.exists(os.path.join(dst, f"{i}.jpg")):
+            shutil.copyfile(f"{REF}/assets/images/{i}.jpg", os.path.join(dst, f"{i}.jpg"))
+    cl = os.path.join(dst, "clouds_all.npz")
+    if not os.path.exists(cl):
+        clouds = {f"c{i}": lo.read_pcd(f"{REF}/assets/clouds/{i}.pcd") for i in range(10)}
+        clouds["background"] = lo.read_pcd(f"{REF}/assets/clouds/background.pcd")[::4].copy()
+        np.savez_compressed(cl, **clouds)
+
+
 def make_pcd_fixtures():
     """tests/golden/pcd/: a 1500-point prefix of assets/clouds/0.pcd (ASCII), an ASCII file exercising the number
     grammar (decimals, exponents, signs, CRLF, an extra column, nan / inf, missing final newline) and a binary file
@@ -142,6 +189,11 @@ def make_pcd_fixtures():
     open(os.path.join(out_dir, "ixyz_binary.pcd"), "wb").write(hdr.encode() + rec.tobytes())
     np.save(os.path.join(out_dir, "ixyz_binary_expected.npy"), xyz)
 
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "all":
+    make_all_assets()
+    copy_assets()
+    sys.exit(0)
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "jpeg":

@@ -262,3 +262,61 @@ def test_whole_chain_jpeg_detect_locate_track():
     fused = rr.run_once(det, loc, img, clouds["c0"], tracker=trk, timestamp_ns=t)
     assert len(fused) == len(robots)
     assert [r.track_id for r in fused if r.isDetected() and r.isLocated()] == [r.track_id for r in located]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# NMS + restore kernel on synthetic candidates (rmr_postprocess_selftest): the cases real frames never produce
+# ---------------------------------------------------------------------------------------------------------------
+def _nms_check(cand, thresh=0.65):
+    got = rr.postprocess_selftest(cand, thresh)
+    keep = do.nms(cand.astype(np.float32), thresh, 0.0)        # every row is already above the score threshold
+    assert np.array_equal(got, cand[keep].astype(np.float32))   # survivors, in anchor order, untouched (identity restore)
+    return keep
+
+
+def test_nms_kernel_suppression_chain_is_all_pairs_not_greedy():
+    """A suppresses B, B would suppress C: greedy NMS keeps C, the reference's all-pairs rule kills it
+    (NMSKernel compares every row with every column whatever became of the column, SURVEY B#5)."""
+    cand = np.array([[0, 0, 100, 100, 0, 0.9], [20, 0, 100, 100, 0, 0.8], [40, 0, 100, 100, 0, 0.7]], np.float32)
+    keep = _nms_check(cand, 0.6)
+    assert keep.tolist() == [0]
+
+
+def test_nms_kernel_ties_labels_and_order():
+    rng = np.random.default_rng(5)
+    cand = []
+    for c in range(40):                                   # clusters with equal confidences and mixed labels
+        x, y = rng.uniform(5, 600, 2)     # away from 0: restoreDetection clamps negative corners
+        for k in range(int(rng.integers(1, 6))):
+            cand.append([x + rng.uniform(-2, 2), y + rng.uniform(-2, 2), 40, 40, float(rng.integers(0, 3)),
+                         float(rng.choice([0.5, 0.6, 0.6, 0.9]))])
+    cand = np.array(cand, np.float32)
+    cand = cand[rng.permutation(len(cand))]
+    keep = _nms_check(cand)
+    assert 40 <= len(keep) < len(cand)
+    same = np.array([[10, 10, 20, 20, 1, 0.7]] * 3, np.float32)   # identical boxes, identical confidence: all survive (B#6)
+    assert _nms_check(same).tolist() == [0, 1, 2]
+
+
+def test_nms_kernel_large_random_sets_match_the_oracle():
+    rng = np.random.default_rng(11)
+    for n in (1, 255, 256, 257, 3000):
+        xy = rng.uniform(0, 300, (n, 2))
+        wh = rng.uniform(10, 120, (n, 2))
+        cand = np.concatenate([xy, wh, rng.integers(0, 12, (n, 1)).astype(np.float64), rng.uniform(0.25, 1, (n, 1))], axis=1)
+        _nms_check(cand.astype(np.float32))
+    assert len(rr.postprocess_selftest(np.zeros((0, 6), np.float32), 0.65)) == 0
+
+
+def test_capacities_fail_loudly_instead_of_truncating():
+    """The reference returns every survivor (detector.cu:561-579); running out of room is RMR_ERR_CAPACITY, never a
+    silently shorter (and atomic-order dependent) list."""
+    many = np.tile(np.array([[0, 0, 10, 10, 0, 0.9]], np.float32), (16385, 1))
+    with pytest.raises(rr.CapacityError, match="capacity 16384"):
+        rr.postprocess_selftest(many, 0.65)
+    # product path: with the confidence threshold at 0 every one of the 34 000 anchors is a candidate
+    det = rr.Detector(fx.engine("car"), 1, fx.IMAGE_SIZE, 1, conf_thresh=0.0)
+    with pytest.raises(rr.CapacityError, match="confidence threshold"):
+        det.detect(fx.load_frame(0))
+    det_ok = rr.Detector(fx.engine("car"), 1, fx.IMAGE_SIZE, 1)
+    assert len(det_ok.detect(fx.load_frame(0))) >= 4        # and the library is still usable afterwards

@@ -36,9 +36,17 @@ class CudnnNet:
                 if t.dim() == 4:
                     t = t.contiguous(memory_format=torch.channels_last)
             self.consts[k] = t
+        # arithmetic operands live on the device from the start (integer constants too): nothing is copied per call,
+        # which is also what makes the forward pass capturable into a CUDA graph
+        for n in self.g.nodes:
+            if n.op in ("Mul", "Add", "Sub", "Div", "Concat"):
+                for i in n.inputs:
+                    if i in self.consts and not self.consts[i].is_cuda and device.type == "cuda":
+                        self.consts[i] = self.consts[i].to(device)
         self.inp = self.g.inputs[0].name
         self.out = self.g.outputs[0].name
-        self.flops = 0.0
+        self.static = None
+        self.dynamic = None
 
     @staticmethod
     def _ints(t):
@@ -46,16 +54,40 @@ class CudnnNet:
 
     @torch.no_grad()
     def __call__(self, x):
+        """The first call also folds every node that does not depend on the input (anchor grids, shape arithmetic) and
+        keeps its result on the device, so later calls — and the CUDA-graph capture — run device work only."""
+        first = self.static is None
+        if first:
+            dyn = {self.inp}
+            for n in self.g.nodes:
+                if n.op != "Shape" and any(i in dyn for i in n.inputs):   # shapes are fixed for a fixed input size
+                    dyn.update(n.outputs)
+            self.dynamic = dyn
+            self.static = {}
         env = dict(self.consts)
+        env.update(self.static)
         env[self.inp] = x
         env[""] = None
         for n in self.g.nodes:
+            if not first and not any(o in self.dynamic for o in n.outputs):
+                continue
             ins = [env[i] for i in n.inputs]
             outs = self._run(n, ins)
             if not isinstance(outs, (tuple, list)):
                 outs = (outs,)
             for name, val in zip(n.outputs, outs):
+                if first and name not in self.dynamic and isinstance(val, torch.Tensor) and val.is_floating_point():
+                    val = val.to(self.dev)
                 env[name] = val
+                if first and name not in self.dynamic:
+                    self.static[name] = val
+        if first and self.dev.type == "cuda":
+            # folded operands of device arithmetic move to the device once (integer ones too): no copies per call
+            for n in self.g.nodes:
+                if n.op in ("Mul", "Add", "Sub", "Div", "Concat") and any(o in self.dynamic for o in n.outputs):
+                    for i in n.inputs:
+                        if i in self.static and isinstance(self.static[i], torch.Tensor) and not self.static[i].is_cuda:
+                            self.static[i] = self.static[i].to(self.dev)
         return env[self.out]
 
     def _same_device(self, ins):
