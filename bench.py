@@ -6,7 +6,8 @@ Workload at N=1: BASELINE config[1] "single 1920x1080 frame + 100k-pt cloud, car
 mode): Locator.update + cluster overlapped with RobotDetector.detect (car net, per-ROI armor net), then
 Locator.search.
 N>1: one process per GPU (torchrun), one independent camera+LiDAR stream per rank (weak scaling,
-BASELINE config[3]) and one NCCL all-gather of the fixed-size robot position block per step.
+BASELINE config[3]) and one NCCL all-gather of the fixed-size robot position block per step, issued by the
+library itself (rmr_comm_publish, csrc/comm.cu) on its own stream.
 
   value  frames/s with frame + cloud already resident in HBM (device-pointer entry points)
   e2e    same metric through the public host-buffer API: pinned host frame + cloud, H2D inside
@@ -197,18 +198,20 @@ def config_dict(world):
             "parallelism": f"dp{world} (stream per GPU)"}
 
 
-def throughput_leg(torch, rr, fx, dev, local_rank, stream, loc_stream, bg, cloud, peak_tf, frames=16, size=1280, steps=10, warmup=3):
+def throughput_leg(torch, rr, fx, dev, local_rank, stream, loc_stream, bg, cloud, peak_tf, frames=16, size=1280, steps=10, warmup=3,
+                   label="BASELINE config[2]", sync=None):
     """BASELINE config[2]: `frames` camera + LiDAR streams per step (rmr_run_batch): the car network batched over the
     frames, the armor network over all their ROIs, one Locator per stream.  Inputs resident in HBM, two batches rotated
     (2 x 79 MB of frames > L2)."""
     import cv2
-    img = cv2.resize(fx.load_frame(0), (size, size), interpolation=cv2.INTER_LINEAR)
-    det = rr.RobotDetector(fx.engine("car"), fx.engine("armor"), (size, size), fx.CLASS_NUM, fx.MAX_BATCH, fx.OPT_BATCH,
+    fw, fh = (size, size) if isinstance(size, int) else size
+    img = cv2.resize(fx.load_frame(0), (fw, fh), interpolation=cv2.INTER_LINEAR)
+    det = rr.RobotDetector(fx.engine("car"), fx.engine("armor"), (fw, fh), fx.CLASS_NUM, fx.MAX_BATCH, fx.OPT_BATCH,
                            device=local_rank, frames=frames)
     det.set_stream(stream.cuda_stream)
     locs = []
     for _ in range(frames):
-        loc = rr.Locator(size, size, fx.scaled_intrinsic(size, size), fx.LIDAR_TO_CAMERA, fx.WORLD_TO_CAMERA, device=local_rank)
+        loc = rr.Locator(fw, fh, fx.scaled_intrinsic(fw, fh), fx.LIDAR_TO_CAMERA, fx.WORLD_TO_CAMERA, device=local_rank)
         loc.set_stream(loc_stream.cuda_stream)
         loc.update(bg[: 1 << 20])
         locs.append(loc)
@@ -220,10 +223,12 @@ def throughput_leg(torch, rr, fx, dev, local_rank, stream, loc_stream, bg, cloud
     def step(i):
         j = (i % pool) * frames
         loc_stream.wait_stream(stream)
-        return rr.run_batch_records(det, locs, fr[j].data_ptr(), True, frames, size, size, size * 3, cl[j].data_ptr(), True, npts, 12)
+        return rr.run_batch_records(det, locs, fr[j].data_ptr(), True, frames, fw, fh, fw * 3, cl[j].data_ptr(), True, npts, 12)
 
     for i in range(warmup):
         step(i)
+    if sync is not None:
+        sync()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     car_ms = armor_ms = 0.0
@@ -238,8 +243,8 @@ def throughput_leg(torch, rr, fx, dev, local_rank, stream, loc_stream, bg, cloud
     st = det.last_stats()
     conv_ms = (car_ms + armor_ms) / steps
     tf = st["conv_flops"] / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    return {"value": frames * steps / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms / steps, "frames_per_step": frames,
-            "workload": f"BASELINE config[2]: {frames} streams of {size}x{size} frames + {npts // 1000}k-pt clouds per step, one GPU, "
+    return {"value": frames * steps / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms / steps, "frames_per_step": frames, "ms_total": ms,
+            "workload": f"{label}: {frames} streams of {fw}x{fh} frames + {npts // 1000}k-pt clouds per step and GPU, "
                         "inputs resident in HBM", "robots_per_frame": [int(c) for c in counts][:4],
             "rois_per_step": int(sum(counts)),
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
@@ -252,7 +257,6 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     import rm_radar_b200 as rr
     from rm_radar_b200 import _lib
-    from rm_radar_b200 import dist as rdist
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -278,42 +282,21 @@ def run_ours(args, rank, world, local_rank):
     frames_pin = torch.from_numpy(frame).unsqueeze(0).repeat(POOL, 1, 1, 1).contiguous().pin_memory()
     clouds_pin = torch.from_numpy(cloud).unsqueeze(0).repeat(POOL, 1, 1).contiguous().pin_memory()
     fbytes, cbytes = frame.nbytes, cloud.nbytes
-    gather_in = torch.zeros(fx.MAX_BATCH, 8, device=dev)
-    gather_out = torch.zeros(world * fx.MAX_BATCH, 8, device=dev) if world > 1 else None
-    pos_pin = torch.zeros(fx.MAX_BATCH, 8).pin_memory()
-    comm_stream = torch.cuda.Stream(device=dev)
     lib = _lib.load()
 
-    # N>1: the exchange (pack -> pinned block -> H2D -> NCCL all-gather on its own stream) is CPU work of ~0.1 ms;
-    # a worker thread does it while the main thread is inside the next rmr_run_once call (ctypes drops the GIL),
-    # so it costs the stream nothing.  Records are snapshotted because the detector reuses its record array.
-    import queue
-    jobs: "queue.Queue" = queue.Queue()
-
-    def publisher():
-        torch.cuda.set_device(local_rank)
-        while True:
-            job = jobs.get()
-            if job is None:
-                jobs.task_done()
-                return
-            snap, n = job
-            comm_stream.synchronize()        # the previous copy has left the pinned block
-            rdist.pack_records(snap, n, fx.MAX_BATCH, out=pos_pin)
-            with torch.cuda.stream(comm_stream):
-                gather_in.copy_(pos_pin, non_blocking=True)
-                rdist.all_gather_records(gather_in, gather_out)
-            jobs.task_done()
-
-    rec_array_t = type(det._recs)
+    # N>1: the exchange lives in the library (rmr_comm_*, csrc/comm.cu): pack -> pinned block -> H2D -> ncclAllGather ->
+    # D2H, all enqueued on the communicator's own stream by one C call that returns at once, so it overlaps the next
+    # frame.  torch.distributed only hands rank 0's NCCL id to the other ranks (and times the run: barrier + max).
+    comm = None
     if world > 1:
-        threading.Thread(target=publisher, daemon=True).start()
+        ident = [rr.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        comm = rr.Comm(ident[0], rank, world, device=local_rank, max_robots=fx.MAX_BATCH)
 
     def publish(recs, n):
         """world-frame robot positions of this rank -> fixed-size block -> one NCCL all-gather (N>1)."""
-        if world == 1:
-            return
-        jobs.put((rec_array_t.from_buffer_copy(recs), n))
+        if comm is not None:
+            comm.publish(recs, n, stream.cuda_stream)
 
     conv_acc = [0.0, 0.0, 0]
     step_stats = {}
@@ -340,7 +323,8 @@ def run_ours(args, rank, world, local_rank):
         for i in range(warmup):
             fn(i)
         if world > 1:
-            jobs.join()      # collectives keep one order on every rank: no all-gather may trail the barrier
+            if comm is not None and warmup > 0:
+                comm.collect()   # collectives keep one order on every rank: no all-gather may trail the barrier
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -351,9 +335,9 @@ def run_ours(args, rank, world, local_rank):
         for i in range(steps):
             n = fn(warmup + i)
             marks[i].record(stream)
-        if world > 1:
-            jobs.join()                      # every step's exchange has been issued ...
-        stream.wait_stream(comm_stream)      # ... and belongs to the timed region
+        if comm is not None and steps > 0:
+            gathered = comm.collect()        # the last step's exchange belongs to the timed region
+            assert gathered.shape[0] == world
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -445,8 +429,6 @@ def run_ours(args, rank, world, local_rank):
         finally:
             torch.cuda.set_stream(stream)
 
-    if world > 1:
-        jobs.put(None)                       # stop the publisher thread
     if rank != 0:
         return
     value = world * args.steps / (ms_res * 1e-3)
@@ -497,6 +479,41 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_config4(args, rank, world, local_rank):
+    """BASELINE config[4]: 3840x2160 frames + 1M-point clouds, a batch of 32 streams sharded over the GPUs (32 / N per
+    rank, no data-path collective: the path shards by stream); value = 32 * steps / max-over-ranks time."""
+    import torch
+    import torch.distributed as dist
+    import rm_radar_b200 as rr
+    from tests import fixtures as fx
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    total, w4, h4, npts = 32, 3840, 2160, 1_000_000
+    frames = total // world
+    bg, cloud, _ = fx.synthetic_scene(npts, 1 + rank, w=w4, h=h4)
+    stream = torch.cuda.Stream(device=dev)
+    loc_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    steps = max(1, min(args.steps, 10))
+    r = throughput_leg(torch, rr, fx, dev, local_rank, stream, loc_stream, bg, np.ascontiguousarray(cloud), peaks()[0], frames=frames,
+                       size=(w4, h4), steps=steps, warmup=3, label="BASELINE config[4]",
+                       sync=(dist.barrier if world > 1 else None))
+    ms = torch.tensor([r["ms_total"]], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        emit({"metric": "detect+locate frames/sec", "value": total * steps / (float(ms.item()) * 1e-3), "unit": "frames/s",
+              "n_gpus": world, "steps": steps, "warmup": 3, "ms_per_step": float(ms.item()) / steps, "higher_is_better": True,
+              "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+              "config": {"workload": f"BASELINE config[4]: {w4}x{h4} frames + 1M-pt clouds, batch {total} sharded {frames} per GPU over {world} GPU(s)",
+                         "parallelism": f"dp{world} (streams sharded, no data-path collective)"},
+              "per_rank0": {k: r[k] for k in ("value", "ms_per_step", "rois_per_step", "roofline")}})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -506,12 +523,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-throughput", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=1, help="1: the headline (BASELINE config[1], + config[2] / [3] legs); 4: config[4]")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     own_stdout()
-    if args.impl == "reference":
+    if args.config == 4 and args.impl != "reference":
+        run_config4(args, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)

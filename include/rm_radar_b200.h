@@ -57,6 +57,7 @@ typedef struct rmr_robot {
 typedef struct rmr_detector rmr_detector_t;
 typedef struct rmr_robot_detector rmr_robot_detector_t;
 typedef struct rmr_locator rmr_locator_t;
+typedef struct rmr_comm rmr_comm_t;
 
 const char* rmr_last_error(void);
 int rmr_device_count(int* count);
@@ -261,6 +262,25 @@ int rmr_run_batch(rmr_robot_detector_t* d, rmr_locator_t* const* locators, int n
  * detector.cu:315-360, 561-579).  Survivors come back in anchor order.  More candidates than the internal capacity:
  * RMR_ERR_CAPACITY. */
 int rmr_postprocess_selftest(const float* candidates, int n, float nms_thresh, rmr_detection_t* out, int capacity, int* count);
+
+/* ---- multi-GPU exchange (one process per GPU, one camera + LiDAR stream per rank) ------------------
+ * The path shards by stream with no data-path collective; the only exchange is one NCCL all-gather per step of the
+ * fixed-size block of world-frame robot records: 8 floats per robot, max_robots rows per rank,
+ *   [valid, label (-1 = undetected), confidence, is_located, x, y, z (metres, world), rect area].
+ * The reference has no distributed code; this is what SampleRadar would call after runOnce on every GPU.
+ * NCCL is loaded at run time (libnccl.so.2); rank 0 makes the id and the host program hands it to the other ranks. */
+#define RMR_COMM_ID_BYTES 128
+#define RMR_RECORD_FLOATS 8
+int rmr_comm_unique_id(uint8_t* id /* [RMR_COMM_ID_BYTES] */);
+int rmr_comm_create(rmr_comm_t** out, const uint8_t* id, int rank, int world, int device, int max_robots);
+void rmr_comm_destroy(rmr_comm_t* c);
+/* pack this rank's records and enqueue upload + all-gather + download on the communicator's stream; returns at once.
+ * after_stream (may be NULL): a CUDA stream whose work so far the exchange is ordered behind */
+int rmr_comm_publish(rmr_comm_t* c, const rmr_robot_t* robots, int n, void* after_stream);
+/* wait for the last publish; out is [world][max_robots][RMR_RECORD_FLOATS] */
+int rmr_comm_collect(rmr_comm_t* c, float* out);
+/* the packing alone (host, no GPU): one rank's block [max_robots][RMR_RECORD_FLOATS] */
+int rmr_comm_pack(const rmr_robot_t* robots, int n, int max_robots, float* block);
 
 /* planning aid (tests/tools only, no GPU needed): the launch plan the tcgen05 conv would use for one layer.
  * out[16] = version (1 = conv.cu, 2 = conv2.cu), block_n, splits, halo, m_tiles, ctas, tiles per CTA,

@@ -19,7 +19,7 @@ import numpy as np
 from . import _lib
 from ._lib import CapacityError, RadarError  # noqa: F401
 
-__all__ = ["Detector", "RobotDetector", "Locator", "Robot", "Detection", "Label", "RadarError",
+__all__ = ["Detector", "RobotDetector", "Locator", "Robot", "Detection", "Label", "RadarError", "Comm",
            "engine_path_for", "run_once", "run_once_records"]
 
 
@@ -623,6 +623,47 @@ def conv_selftest(n, h, w, cin, cout, k, stride, act=1, residual=0, out_f32=0, s
     _lib.check(lib.rmr_conv_selftest(n, h, w, cin, cout, k, stride, act, residual, out_f32, seed, iters,
                                      C.byref(d), C.byref(r), C.byref(ms)))
     return d.value, r.value, ms.value
+
+
+class Comm:
+    """The multi-GPU exchange inside the library (rmr_comm_*): one NCCL all-gather per step of every rank's block of
+    robot records [max_robots, 8] = [valid, label, confidence, is_located, x, y, z, rect area]."""
+
+    ID_BYTES, RECORD_FLOATS = 128, 8
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * Comm.ID_BYTES)()
+        _lib.check(_lib.load().rmr_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int = 0, max_robots: int = 20):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        buf = (C.c_uint8 * Comm.ID_BYTES).from_buffer_copy(unique_id)
+        _lib.check(self._lib.rmr_comm_create(C.byref(self._h), buf, rank, world, device, max_robots))
+        self.rank, self.world, self.max_robots = rank, world, max_robots
+        self._out = np.zeros((world, max_robots, Comm.RECORD_FLOATS), np.float32)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.rmr_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def publish(self, recs, n: int, after_stream: int = 0):
+        """recs: the ctypes RobotRec array rmr_run_once filled; returns at once (the exchange runs on its own stream)."""
+        _lib.check(self._lib.rmr_comm_publish(self._h, recs, n, C.c_void_p(after_stream)))
+
+    def collect(self) -> np.ndarray:
+        """[world, max_robots, 8] of the last publish (waits for it)."""
+        _lib.check(self._lib.rmr_comm_collect(self._h, self._out.ctypes.data))
+        return self._out
+
+    @staticmethod
+    def pack(recs, n: int, max_robots: int) -> np.ndarray:
+        out = np.zeros((max_robots, Comm.RECORD_FLOATS), np.float32)
+        _lib.check(_lib.load().rmr_comm_pack(recs, n, max_robots, out.ctypes.data))
+        return out
 
 
 def postprocess_selftest(candidates: np.ndarray, nms_thresh: float) -> np.ndarray:

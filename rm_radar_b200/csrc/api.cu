@@ -10,6 +10,7 @@
 #include "jpeg.h"
 #include "pcd.h"
 #include "track.h"
+#include "comm.h"
 
 using namespace rmr;
 
@@ -28,6 +29,9 @@ struct rmr_tracker {
 struct rmr_jpeg_decoder {
     std::unique_ptr<JpegDecoder> impl;
     cudaEvent_t decoded = nullptr;
+};
+struct rmr_comm {
+    std::unique_ptr<Comm> impl;
 };
 struct rmr_locator {
     std::unique_ptr<Locator> impl;
@@ -833,6 +837,46 @@ int rmr_conv_timeline(int n, int h_in, int w_in, int cin, int cout, int k, int s
         RMR_CUDA(cudaMemcpy(out, d_dbg, sizeof(long long) * 64 * std::min(ctas, capacity_ctas), cudaMemcpyDeviceToHost));
         cudaStreamDestroy(s);
         cudaFree(d_in); cudaFree(d_w); cudaFree(d_out); cudaFree(d_bias); cudaFree(d_dbg); cudaFree(d_scratch);
+    });
+}
+
+// ---------------------------------------------------------------- multi-GPU exchange
+int rmr_comm_unique_id(uint8_t* id) {
+    return guarded([&] {
+        if (!id) throw std::invalid_argument("null argument");
+        comm_unique_id(id);
+    });
+}
+
+int rmr_comm_create(rmr_comm_t** out, const uint8_t* id, int rank, int world, int device, int max_robots) {
+    return guarded([&] {
+        if (!out || !id) throw std::invalid_argument("null argument");
+        auto h = std::make_unique<rmr_comm>();
+        h->impl = std::make_unique<Comm>(id, rank, world, device, max_robots);
+        *out = h.release();
+    });
+}
+
+void rmr_comm_destroy(rmr_comm_t* c) { delete c; }
+
+int rmr_comm_publish(rmr_comm_t* c, const rmr_robot_t* robots, int n, void* after_stream) {
+    return guarded([&] {
+        if (!c || (!robots && n > 0)) throw std::invalid_argument("null argument");
+        c->impl->publish(robots, n, static_cast<cudaStream_t>(after_stream));
+    });
+}
+
+int rmr_comm_collect(rmr_comm_t* c, float* out) {
+    return guarded([&] {
+        if (!c || !out) throw std::invalid_argument("null argument");
+        c->impl->collect(out);
+    });
+}
+
+int rmr_comm_pack(const rmr_robot_t* robots, int n, int max_robots, float* block) {
+    return guarded([&] {
+        if ((!robots && n > 0) || !block || max_robots < 1) throw std::invalid_argument("null argument");
+        Comm::pack(robots, n, max_robots, block);
     });
 }
 

@@ -109,3 +109,25 @@ def test_jpeg_header_parser_scope_matches_the_oracle():
     for bad in (b"", b"\xff\xd8", b"not a jpeg", open(os.path.join(JPEG_DIR, "photo_420_q90.jpg"), "rb").read()[:100]):
         with pytest.raises(ValueError):
             rr.jpeg_info(bad)
+
+
+def test_comm_pack_matches_the_python_record_layout():
+    """rmr_comm_pack (the block csrc/comm.cu all-gathers) == rm_radar_b200.dist.pack_records, field by field."""
+    import numpy as np
+    import rm_radar_b200 as rr
+    from rm_radar_b200 import dist
+    rng = np.random.default_rng(3)
+    recs = (_lib.RobotRec * 6)()
+    for i in range(5):
+        r = recs[i]
+        r.has_rect = 1
+        for k in range(4):
+            r.rect[k] = float(rng.uniform(1, 500))
+        r.is_detected = int(i % 2)
+        r.label = int(rng.integers(0, 12))
+        r.confidence = float(rng.uniform(0.5, 1))
+        r.is_located = int(i % 3 != 0)
+        for k in range(3):
+            r.location[k] = float(rng.uniform(-10, 10))
+    for n, cap in ((5, 6), (5, 3), (0, 4)):
+        assert np.array_equal(rr.Comm.pack(recs, n, cap), dist.pack_records(recs, n, cap).numpy())

@@ -42,7 +42,14 @@ def detector():
 
 
 @pytest.mark.parametrize("i", range(10))
-def test_detect_and_locate_match_the_oracle_on_asset_pair(detector, i):
+def test_detect_and_locate_match_the_oracle_on_asset_pair(i):
+    """A fresh detector per pair, like the oracle run that wrote the expected values: in the reference-compatible
+    letterbox mode the u8 staging buffer is persistent (SURVEY B#1: bytes of earlier ROIs survive where nothing is
+    written), so a detector's history reaches the armour confidences in the fourth decimal — frame 8 has an armour at
+    0.4987 against the 0.50 threshold."""
+    if not fx.have_models():
+        pytest.skip("engines missing")
+    detector = rr.RobotDetector(fx.engine("car"), fx.engine("armor"), fx.IMAGE_SIZE, fx.CLASS_NUM, fx.MAX_BATCH, fx.OPT_BATCH)
     exp = np.load(EXPECTED)
     img = _frame(i)
     clouds = _clouds()
@@ -120,5 +127,6 @@ def test_armor_head_matches_the_fp32_oracle_on_real_rois(detector):
         assert got[k].shape == ref.shape and ref.shape[0] == 4 + fx.CLASS_NUM
         assert np.abs(got[k][4:] - ref[4:]).max() < 4e-3                    # every class score of every anchor
         hot = ref[4:].max(axis=0) > 0.05
-        assert np.abs(got[k][:4, hot] - ref[:4, hot]).max() < 0.25          # boxes where there is anything to box
-        assert (got[k][4:, hot].argmax(axis=0) == ref[4:, hot].argmax(axis=0)).all()   # class-exact
+        if hot.any():
+            assert np.abs(got[k][:4, hot] - ref[:4, hot]).max() < 0.25          # boxes where there is anything to box
+            assert (got[k][4:, hot].argmax(axis=0) == ref[4:, hot].argmax(axis=0)).all()   # class-exact
