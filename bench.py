@@ -429,6 +429,15 @@ def run_ours(args, rank, world, local_rank):
         finally:
             torch.cuda.set_stream(stream)
 
+    # orderly collective shutdown on EVERY rank before rank 0 goes on alone (a rank that simply exits while another is
+    # still inside a NCCL teardown leaves it hanging)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        if comm is not None:
+            comm.close()
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     value = world * args.steps / (ms_res * 1e-3)
@@ -475,8 +484,6 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {e}"}
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def run_config4(args, rank, world, local_rank):

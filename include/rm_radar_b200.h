@@ -273,6 +273,9 @@ int rmr_postprocess_selftest(const float* candidates, int n, float nms_thresh, r
 #define RMR_RECORD_FLOATS 8
 int rmr_comm_unique_id(uint8_t* id /* [RMR_COMM_ID_BYTES] */);
 int rmr_comm_create(rmr_comm_t** out, const uint8_t* id, int rank, int world, int device, int max_robots);
+/* orderly collective shutdown: every rank calls it at the same point of the program (waits for the exchange in flight,
+ * then ncclCommDestroy).  rmr_comm_destroy on a communicator that was not closed aborts it (never waits for a peer). */
+int rmr_comm_close(rmr_comm_t* c);
 void rmr_comm_destroy(rmr_comm_t* c);
 /* pack this rank's records and enqueue upload + all-gather + download on the communicator's stream; returns at once.
  * after_stream (may be NULL): a CUDA stream whose work so far the exchange is ordered behind */

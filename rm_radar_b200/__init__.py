@@ -650,6 +650,11 @@ class Comm:
             self._lib.rmr_comm_destroy(self._h)
             self._h = C.c_void_p()
 
+    def close(self):
+        """Orderly shutdown; every rank calls it at the same point of the program."""
+        if getattr(self, "_h", None) and self._h.value:
+            _lib.check(self._lib.rmr_comm_close(self._h))
+
     def publish(self, recs, n: int, after_stream: int = 0):
         """recs: the ctypes RobotRec array rmr_run_once filled; returns at once (the exchange runs on its own stream)."""
         _lib.check(self._lib.rmr_comm_publish(self._h, recs, n, C.c_void_p(after_stream)))

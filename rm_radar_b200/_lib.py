@@ -45,7 +45,7 @@ SYMBOLS = [
     "rmr_locator_cluster", "rmr_locator_search", "rmr_locator_update_pcd", "rmr_pcd_parse", "rmr_locator_load_background", "rmr_locator_set_stream", "rmr_locator_image_size",
     "rmr_locator_read_image", "rmr_locator_stats", "rmr_locator_read_foreground",
     "rmr_run_once", "rmr_conv_selftest", "rmr_conv_timeline", "rmr_conv_plan", "rmr_postprocess_selftest",
-    "rmr_comm_unique_id", "rmr_comm_create", "rmr_comm_destroy", "rmr_comm_publish", "rmr_comm_collect", "rmr_comm_pack",
+    "rmr_comm_unique_id", "rmr_comm_create", "rmr_comm_close", "rmr_comm_destroy", "rmr_comm_publish", "rmr_comm_collect", "rmr_comm_pack",
     "rmr_tracker_create", "rmr_tracker_destroy", "rmr_tracker_update", "rmr_tracker_tracks", "rmr_auction",
     "rmr_jpeg_decoder_create", "rmr_jpeg_decoder_destroy", "rmr_jpeg_decoder_set_stream", "rmr_jpeg_info", "rmr_jpeg_decode",
     "rmr_jpeg_decode_device", "rmr_jpeg_decoder_status", "rmr_jpeg_decoder_read_coefficients", "rmr_jpeg_decoder_profile", "rmr_robot_detector_detect_jpeg",
@@ -145,6 +145,7 @@ def load():
     lib.rmr_postprocess_selftest.argtypes = [vp, ci, cf, vp, ci, P(ci)]
     lib.rmr_comm_unique_id.argtypes = [vp]
     lib.rmr_comm_create.argtypes = [P(vp), vp, ci, ci, ci, ci]
+    lib.rmr_comm_close.argtypes = [vp]
     lib.rmr_comm_destroy.argtypes = [vp]
     lib.rmr_comm_destroy.restype = None
     lib.rmr_comm_publish.argtypes = [vp, vp, ci, vp]

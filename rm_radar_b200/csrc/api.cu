@@ -857,6 +857,13 @@ int rmr_comm_create(rmr_comm_t** out, const uint8_t* id, int rank, int world, in
     });
 }
 
+int rmr_comm_close(rmr_comm_t* c) {
+    return guarded([&] {
+        if (!c) throw std::invalid_argument("null argument");
+        c->impl->close();
+    });
+}
+
 void rmr_comm_destroy(rmr_comm_t* c) { delete c; }
 
 int rmr_comm_publish(rmr_comm_t* c, const rmr_robot_t* robots, int n, void* after_stream) {

@@ -17,6 +17,7 @@ struct NcclUniqueId { char internal[kUniqueIdBytes]; };
 using GetUniqueIdFn = int (*)(NcclUniqueId*);
 using CommInitRankFn = int (*)(void**, int, NcclUniqueId, int);
 using CommDestroyFn = int (*)(void*);
+using CommAbortFn = int (*)(void*);
 using AllGatherFn = int (*)(const void*, void*, size_t, int, void*, cudaStream_t);
 using GetErrorStringFn = const char* (*)(int);
 constexpr int kNcclFloat = 7;
@@ -25,6 +26,7 @@ struct Nccl {
     GetUniqueIdFn get_unique_id = nullptr;
     CommInitRankFn comm_init_rank = nullptr;
     CommDestroyFn comm_destroy = nullptr;
+    CommAbortFn comm_abort = nullptr;
     AllGatherFn all_gather = nullptr;
     GetErrorStringFn error_string = nullptr;
 };
@@ -43,6 +45,7 @@ const Nccl& nccl() {
         api.get_unique_id = reinterpret_cast<GetUniqueIdFn>(dlsym(h, "ncclGetUniqueId"));
         api.comm_init_rank = reinterpret_cast<CommInitRankFn>(dlsym(h, "ncclCommInitRank"));
         api.comm_destroy = reinterpret_cast<CommDestroyFn>(dlsym(h, "ncclCommDestroy"));
+        api.comm_abort = reinterpret_cast<CommAbortFn>(dlsym(h, "ncclCommAbort"));
         api.all_gather = reinterpret_cast<AllGatherFn>(dlsym(h, "ncclAllGather"));
         api.error_string = reinterpret_cast<GetErrorStringFn>(dlsym(h, "ncclGetErrorString"));
         if (!api.get_unique_id || !api.comm_init_rank || !api.comm_destroy || !api.all_gather || !api.error_string)
@@ -96,10 +99,24 @@ Comm::Comm(const uint8_t id[kUniqueIdBytes], int rank, int world, int device, in
     RMR_CUDA(cudaMalloc(&dev_out_, block * world));
 }
 
+// Orderly shutdown, called by every rank at the same point of the program: waits for the exchange in flight, then
+// ncclCommDestroy.  A communicator that is merely dropped (process exit, exception) is aborted instead, which never
+// waits for a peer that may already be gone.
+void Comm::close() {
+    if (!comm_) return;
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    nccl().comm_destroy(comm_);
+    comm_ = nullptr;
+}
+
 Comm::~Comm() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
-    if (comm_) nccl().comm_destroy(comm_);
+    if (comm_) {
+        if (nccl().comm_abort) nccl().comm_abort(comm_);
+        else nccl().comm_destroy(comm_);
+    }
     cudaFreeHost(pinned_in_); cudaFreeHost(pinned_out_); cudaFree(dev_in_); cudaFree(dev_out_);
     if (ready_) cudaEventDestroy(ready_);
     if (done_) cudaEventDestroy(done_);

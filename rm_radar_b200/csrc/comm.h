@@ -30,6 +30,8 @@ public:
     void publish(const rmr_robot* robots, int n, cudaStream_t after);
     // wait for the last publish and copy out [world][max_robots][8] floats
     void collect(float* out);
+    // collective shutdown (every rank, same program point); the destructor of an unclosed communicator aborts instead
+    void close();
     int world() const { return world_; }
     int rank() const { return rank_; }
     int max_robots() const { return max_robots_; }
