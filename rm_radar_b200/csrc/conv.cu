@@ -650,6 +650,97 @@ __global__ void __launch_bounds__(128) conv_stem_kernel(ConvDesc d) {
     }
 }
 
+
+// Stem, second version: the same 3x3 stride-2 Cin = 3 (stored as 4) convolution as an im2col GEMM on mma.sync
+// (m16n8k16, fp16 operands, fp32 accumulate).  The layer is HBM-bound by nature (armor, batch 7: 23 MB in, 46 MB out,
+// 1.2 GFLOP), so there is nothing for tcgen05 to win; what the SIMT version above spends is FP32 issue slots (1728 FMA
+// per thread) and broadcast LDS.  One warp = 16 consecutive output pixels of a row x all 32 channels: K = 9 taps x 4
+// channels = 36, padded to three k16 steps; an A fragment element pair is one 32-bit load of a pixel's channel pair,
+// the weights sit in 24 registers per thread for the whole kernel, the tile leaves through a padded shared-memory
+// transpose as 16-byte stores (64 contiguous bytes per pixel).
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) conv_stem_mma_kernel(ConvDesc d, int tiles_w, long total_tiles) {
+    __shared__ __align__(16) unsigned char s_tile[4][16 * 80];   // per warp: 16 pixels x (32 ch fp16 + 16 B pad)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    // weights: B[k][n] = w[n][k], k = tap * 4 + ch; fragment registers of kstep s, n-tile j
+    uint32_t bw[3][4][2];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __half* wr = d.w + static_cast<size_t>(8 * j + g) * 36;
+            const int k0 = 16 * s + 2 * q, k1 = k0 + 8;
+            bw[s][j][0] = k0 < 36 ? *reinterpret_cast<const uint32_t*>(wr + k0) : 0u;
+            bw[s][j][1] = k1 < 36 ? *reinterpret_cast<const uint32_t*>(wr + k1) : 0u;
+        }
+    float bias[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { bias[j][0] = d.bias[8 * j + 2 * q]; bias[j][1] = d.bias[8 * j + 2 * q + 1]; }
+    unsigned char* tile = s_tile[warp];
+    const long warps_total = static_cast<long>(gridDim.x) * 4;
+    for (long t = static_cast<long>(blockIdx.x) * 4 + warp; t < total_tiles; t += warps_total) {
+        const int tx = static_cast<int>(t % tiles_w);
+        const long row_id = t / tiles_w;
+        const int oy = static_cast<int>(row_id % d.h_out), n = static_cast<int>(row_id / d.h_out);
+        const int ox0 = tx * 16;
+        const __half* img = d.in + static_cast<size_t>(n) * d.h_in * d.w_in * 4;
+        float c[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f; }
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            uint32_t a[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {            // k half: columns 2q (+8)
+                const int k = 16 * s + 2 * q + 8 * h;
+                const int tap = k >> 2, ch = k & 3;
+                const int iy = 2 * oy - 1 + tap / 3, dxo = tap % 3 - 1;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {        // fragment rows g, g + 8
+                    const int ix = 2 * (ox0 + g + 8 * r) + dxo;
+                    uint32_t v = 0u;
+                    if (k < 36 && iy >= 0 && iy < d.h_in && ix >= 0 && ix < d.w_in)
+                        v = __ldg(reinterpret_cast<const uint32_t*>(img + (static_cast<size_t>(iy) * d.w_in + ix) * 4 + ch));
+                    a[2 * h + r] = v;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_16816(c[j], a, bw[s][j][0], bw[s][j][1]);
+        }
+        // bias + SiLU (h + h tanh(h), h = x / 2) -> fp16 -> padded shared tile [16][80 B]
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                float x0 = c[j][2 * r] + bias[j][0], x1 = c[j][2 * r + 1] + bias[j][1];
+                if (d.act) {
+                    float h0 = 0.5f * x0, h1 = 0.5f * x1, t0, t1;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+                    x0 = fmaf(h0, t0, h0); x1 = fmaf(h1, t1, h1);
+                }
+                *reinterpret_cast<__half2*>(tile + (g + 8 * r) * 80 + (8 * j + 2 * q) * 2) = __floats2half2_rn(x0, x1);
+            }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int prow = g + 8 * r, ox = ox0 + prow;
+            if (ox < d.w_out) {
+                const uint4 v = *reinterpret_cast<const uint4*>(tile + prow * 80 + q * 16);
+                const size_t pix = (static_cast<size_t>(n) * d.h_out + oy) * d.w_out + ox;
+                *reinterpret_cast<uint4*>(static_cast<__half*>(d.out) + pix * d.out_pitch + d.out_coff + q * 8) = v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ---- memory-bound helpers: 8 channels (16 B) per thread, NHWC ----
 __global__ void maxpool5_kernel(const __half* in, int in_pitch, int in_coff, __half* out, int out_pitch,
                                 int out_coff, int n, int h, int w, int c8) {
@@ -1110,7 +1201,14 @@ void launch_conv_umma(const ConvLaunch& l, cudaStream_t s, bool pdl) {
 }
 
 void launch_conv_simt(const ConvDesc& d, cudaStream_t s) {
-    if (d.cin_pad == 4 && d.k == 3 && d.stride == 2 && d.act == 1 && d.res == nullptr && !d.out_f32 &&
+    static const bool stem_mma = [] { const char* e = std::getenv("RMR_STEM_SIMT"); return !(e && e[0] == '1'); }();
+    if (stem_mma && d.cin_pad == 4 && d.k == 3 && d.stride == 2 && d.res == nullptr && !d.out_f32 && d.in_pitch == 4 &&
+        d.in_coff == 0 && d.cout == 32 && d.cout_pad == 32 && d.out_pitch % 8 == 0 && d.out_coff % 8 == 0 && d.dup == nullptr) {
+        const int tiles_w = (d.w_out + 15) / 16;
+        const long total = static_cast<long>(d.n) * d.h_out * tiles_w;
+        const int blocks = static_cast<int>(std::min<long>((total + 3) / 4, 148L * 12));
+        conv_stem_mma_kernel<<<blocks, 128, 0, s>>>(d, tiles_w, total);
+    } else if (d.cin_pad == 4 && d.k == 3 && d.stride == 2 && d.act == 1 && d.res == nullptr && !d.out_f32 &&
         d.in_pitch == 4 && d.in_coff == 0 && (d.cout == 32 || d.cout == 16)) {
         const long total = static_cast<long>(d.n) * d.h_out * ((d.w_out + 1) / 2);
         const int blocks = static_cast<int>((total + 127) / 128);

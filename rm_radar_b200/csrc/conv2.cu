@@ -935,8 +935,11 @@ void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
     p.chunk_bytes = 32u * esize;
     p.sub_bytes = 128u * p.chunk_bytes;
     const int stage_bytes = p.tma_epi ? static_cast<int>(p.sub_bytes) * p.nchunks : 0;
-    const long budget = kSmemMax - 1024 - stage_bytes;
     const int tiles_per_cta = (p.m_tiles + p.gm - 1) / p.gm;
+    // (Capping single-tile CTAs at half an SM of shared memory, so that the next layer's CTA can become resident under
+    // programmatic dependent launch and run its prologue during this layer's tail, was measured and lost: the shallower
+    // ring costs more per k-block than the overlap returns — car 0.53 vs 0.44 ms, armor 0.94 vs 0.79 ms.)
+    const long budget = kSmemMax - 1024 - stage_bytes;
     const long a_units_total = static_cast<long>(tiles_per_cta) * p.units_per_split;   // A units (patches / k-blocks) this CTA ever loads
     const long b_slice = static_cast<long>(kb_cta) * p.b_kb;
     const bool want_resident = env_flag("RMR_B_RESIDENT", true);
