@@ -119,11 +119,11 @@ def ncu_traffic():
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_conv_full.json")))
     if not files:
-        return None
+        return None, None
     try:
-        return json.load(open(files[-1])).get("dram_bytes_per_launch_mean")
+        return json.load(open(files[-1])).get("dram_bytes_per_launch_mean"), os.path.relpath(files[-1], ROOT)
     except Exception:   # noqa: BLE001
-        return None
+        return None, None
 
 
 def peaks():
@@ -454,13 +454,13 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int((stats["kernel_launches"] + locate_launches) * args.steps),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf, "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "frac": achieved_tf / peak_tf, "traffic": ncu_traffic()[0], "peak_source": peak_src,
                      "kernel": "conv_umma_kernel (tcgen05 implicit GEMM), all conv launches of one frame",
                      "flops_per_step": stats["conv_flops"], "conv_ms_per_step": conv_ms,
                      "conv_launches_per_step": conv_launches,
                      "flops_per_launch": stats["conv_flops"] / max(conv_launches, 1),
                      "avg_launch_us": 1e3 * conv_ms / max(conv_launches, 1),
-                     "traffic_note": "mean dram__bytes_read+write per launch, ncu --set full, profiles/r1_conv_full.json",
+                     "traffic_note": f"mean dram__bytes_read+write per launch, ncu --set full, {ncu_traffic()[1]}",
                      "car_net_ms": car_ms_in, "armor_net_ms": armor_ms_in, "armor_batch": k_cars,
                      "timing": "CUDA events on the detector stream around each graph replay, mean over the timed steps",
                      "replayed_alone_ms": {"car": car_ms, "armor": armor_ms},

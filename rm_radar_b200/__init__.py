@@ -135,7 +135,7 @@ class Detector:
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
             self._lib.rmr_detector_destroy(self._h)
-            self._h = C.c_void_p()
+            self._h.value = None
 
     def detect(self, images):
         """One HxWx3 BGR uint8 array → list[Detection]; a sequence of arrays → list[list[Detection]]."""
@@ -254,7 +254,7 @@ class RobotDetector:
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
             self._lib.rmr_robot_detector_destroy(self._h)
-            self._h = C.c_void_p()
+            self._h.value = None
 
     def detect(self, image: np.ndarray) -> list:
         """RobotDetector::detect(const cv::Mat&) — detector.cpp:413-455."""
@@ -346,7 +346,7 @@ class Locator:
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
             self._lib.rmr_locator_destroy(self._h)
-            self._h = C.c_void_p()
+            self._h.value = None
 
     def update(self, cloud):
         """Locator::update — locate.cpp:158-220.  cloud: [n,3] or [n,4] float32 (PointXYZ) or None."""
@@ -648,7 +648,7 @@ class Comm:
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
             self._lib.rmr_comm_destroy(self._h)
-            self._h = C.c_void_p()
+            self._h.value = None
 
     def close(self):
         """Orderly shutdown; every rank calls it at the same point of the program."""

@@ -154,7 +154,7 @@ void Detector::enqueue(const uint8_t* dev_frame, int stride, const Roi* rois, in
                                sizeof(Detection) * kHeadOut, n, cudaMemcpyDeviceToHost, stream_));
     int net_launches = 0;
     net_->plan_stats(n, &net_launches, nullptr, nullptr);
-    last_launches_ = (any_clean ? 1 : 0) + (any_unclean ? 2 : 0) + net_launches + 2;
+    last_launches_ = (any_clean ? 1 : 0) + (any_unclean ? letterbox_compat_launches() : 0) + net_launches + 2;
     pending_ = n;
 }
 

@@ -94,45 +94,49 @@ __device__ __forceinline__ float iou_xywh(const float4 a, const float4 b) {
 // anchor index so that the output order is the reference's anchor order (detector.cu:561-579),
 // then every row is tested against every column (race-free all-pairs rule, Appendix B#5/#6),
 // survivors are compacted in order and un-letterboxed (restoreDetection, detector.cpp:258-268).
-__global__ void __launch_bounds__(256) nms_restore_kernel(const float* __restrict__ cand,
-                                                          const int* __restrict__ cand_count, float* sorted_scratch,
-                                                          const LetterboxGeom* __restrict__ geoms, float nms_thresh,
-                                                          Detection* __restrict__ out, int* __restrict__ out_count,
-                                                          int max_out) {
-    const int img = blockIdx.x;
-    const int n = min(cand_count[img], kMaxCandidates);
-    const float* c = cand + static_cast<size_t>(img) * kMaxCandidates * 8;
-    float* sorted = sorted_scratch + static_cast<size_t>(img) * kMaxCandidates * 8;
-    __shared__ int warp_tot[8];
-    __shared__ int base;
+// Up to kSmemCand candidates (every real frame) the ranked list lives in shared memory, so the
+// two all-pairs loops read broadcast words instead of L1 lines; longer lists use the global scratch.
+constexpr int kSmemCand = 1024;
 
+template <bool kShared>
+__device__ __forceinline__ void nms_restore_body(const float* __restrict__ c, int n, float4* sbox, float4* smeta,
+                                                 int* sanchor, const LetterboxGeom& g, float nms_thresh,
+                                                 Detection* __restrict__ out, int* __restrict__ out_count, int max_out,
+                                                 int* warp_tot, int* base) {
+    if (kShared) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sanchor[i] = __float_as_int(c[i * 8 + 6]);
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float4 b0 = reinterpret_cast<const float4*>(c + i * 8)[0];
         const float4 b1 = reinterpret_cast<const float4*>(c + i * 8)[1];
         const int anchor = __float_as_int(b1.z);
         int rank = 0;
-        for (int j = 0; j < n; ++j) rank += (__float_as_int(c[j * 8 + 6]) < anchor) ? 1 : 0;
-        reinterpret_cast<float4*>(sorted + rank * 8)[0] = b0;
-        reinterpret_cast<float4*>(sorted + rank * 8)[1] = b1;
+        if (kShared) {
+            for (int j = 0; j < n; ++j) rank += (sanchor[j] < anchor) ? 1 : 0;
+        } else {
+            for (int j = 0; j < n; ++j) rank += (__float_as_int(c[j * 8 + 6]) < anchor) ? 1 : 0;
+        }
+        sbox[kShared ? rank : 2 * rank] = b0;
+        smeta[kShared ? rank : 2 * rank] = b1;
     }
-    if (threadIdx.x == 0) base = 0;
+    if (threadIdx.x == 0) *base = 0;
     __syncthreads();
 
-    const LetterboxGeom g = geoms[img];
     for (int i0 = 0; i0 < n; i0 += blockDim.x) {
         const int i = i0 + threadIdx.x;
         bool keep = false;
         float4 box = make_float4(0, 0, 0, 0);
         float label = 0.f, conf = 0.f;
         if (i < n) {
-            box = reinterpret_cast<const float4*>(sorted + i * 8)[0];
-            const float4 m = reinterpret_cast<const float4*>(sorted + i * 8)[1];
+            box = sbox[kShared ? i : 2 * i];
+            const float4 m = smeta[kShared ? i : 2 * i];
             label = m.x; conf = m.y;
             keep = true;
             for (int j = 0; j < n && keep; ++j) {
-                const float4 mj = reinterpret_cast<const float4*>(sorted + j * 8)[1];
+                const float4 mj = smeta[kShared ? j : 2 * j];
                 if (mj.x == label && mj.y > conf) {
-                    const float4 bj = reinterpret_cast<const float4*>(sorted + j * 8)[0];
+                    const float4 bj = sbox[kShared ? j : 2 * j];
                     if (iou_xywh(box, bj) > nms_thresh) keep = false;
                 }
             }
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(256) nms_restore_kernel(const float* __restric
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         if (lane == 0) warp_tot[warp] = __popc(ballot);
         __syncthreads();
-        int off = base;
+        int off = *base;
         for (int w = 0; w < warp; ++w) off += warp_tot[w];
         off += __popc(ballot & ((1u << lane) - 1u));
         if (keep && off < max_out) {
@@ -152,17 +156,42 @@ __global__ void __launch_bounds__(256) nms_restore_kernel(const float* __restric
             d.height = fminf(fmaxf(box.w * g.ratio, 0.f), g.height - d.y);
             d.label = label;
             d.confidence = conf;
-            out[static_cast<size_t>(img) * max_out + off] = d;
+            out[off] = d;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             int t = 0;
             for (int w = 0; w < 8; ++w) t += warp_tot[w];
-            base += t;
+            *base += t;
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) out_count[img] = base;
+    if (threadIdx.x == 0) *out_count = *base;
+}
+
+__global__ void __launch_bounds__(256) nms_restore_kernel(const float* __restrict__ cand,
+                                                          const int* __restrict__ cand_count, float* sorted_scratch,
+                                                          const LetterboxGeom* __restrict__ geoms, float nms_thresh,
+                                                          Detection* __restrict__ out, int* __restrict__ out_count,
+                                                          int max_out) {
+    const int img = blockIdx.x;
+    const int n = min(cand_count[img], kMaxCandidates);
+    const float* c = cand + static_cast<size_t>(img) * kMaxCandidates * 8;
+    __shared__ float4 s_box[kSmemCand];
+    __shared__ float4 s_meta[kSmemCand];
+    __shared__ int s_anchor[kSmemCand];
+    __shared__ int warp_tot[8];
+    __shared__ int base;
+    const LetterboxGeom g = geoms[img];
+    Detection* o = out + static_cast<size_t>(img) * max_out;
+    if (n <= kSmemCand) {
+        nms_restore_body<true>(c, n, s_box, s_meta, s_anchor, g, nms_thresh, o, out_count + img, max_out, warp_tot, &base);
+    } else {
+        // global scratch rows are [box float4][meta float4]: element i of either view sits at float4 index 2 i
+        float4* sorted = reinterpret_cast<float4*>(sorted_scratch + static_cast<size_t>(img) * kMaxCandidates * 8);
+        nms_restore_body<false>(c, n, sorted, sorted + 1, nullptr, g, nms_thresh, o, out_count + img, max_out, warp_tot,
+                                &base);
+    }
 }
 
 }  // namespace

@@ -15,6 +15,8 @@
 // through the same persistent u8 staging buffer as the reference (two launches).
 #include "preprocess.h"
 
+#include <cstdlib>
+
 namespace rmr {
 
 namespace {
@@ -103,7 +105,43 @@ __global__ void __launch_bounds__(256) letterbox_blob_kernel(const LetterboxGeom
     reinterpret_cast<uint2*>(out)[static_cast<size_t>(blockIdx.y) * out_w * out_h + idx] = pack_rgb(s[0], s[1], s[2]);
 }
 
+// Both stages in one pass.  Stage 1 writes the bordered pixel (x', y') at bytes 3 (y' stride_w + x') of the slot, stage 2
+// reads bytes 3 idx for network pixel idx: the two meet at idx = y' stride_w + x', so the thread of network pixel idx
+// owns exactly the staging bytes it needs — it stores the freshly sampled pixel there (later calls must see it) or, where
+// stage 1 writes nothing, picks up the stale bytes of earlier calls, and converts.  Same arithmetic, one launch, the
+// staging buffer is written once and read only where it is stale.
+__global__ void __launch_bounds__(256) letterbox_compat_kernel(const unsigned char* __restrict__ frame, int stride,
+                                                               const LetterboxGeom* __restrict__ geoms,
+                                                               unsigned char* __restrict__ staging, __half* __restrict__ out,
+                                                               int out_w, int out_h) {
+    const LetterboxGeom g = geoms[blockIdx.y];
+    if (g.clean) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= out_w * out_h) return;
+    unsigned char* slot = staging + (static_cast<size_t>(blockIdx.y) * out_w * out_h + idx) * 3;
+    const int y = idx / g.stride_w, x = idx - y * g.stride_w;
+    unsigned char v[3];
+    if (x < g.bw && y < g.bh) {
+        const int rx = x - g.left, ry = y - g.top;
+        v[0] = v[1] = v[2] = 128;
+        if (rx >= 0 && rx < g.pw && ry >= 0 && ry < g.ph) {
+            const unsigned char* src = frame + static_cast<size_t>(g.src_y) * stride + g.src_x * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = sample_u8(src, stride, g.src_w, g.src_h, g.pw, g.ph, rx, ry, c);
+        }
+        slot[0] = v[0]; slot[1] = v[1]; slot[2] = v[2];
+    } else {
+        v[0] = slot[0]; v[1] = slot[1]; v[2] = slot[2];
+    }
+    reinterpret_cast<uint2*>(out)[static_cast<size_t>(blockIdx.y) * out_w * out_h + idx] = pack_rgb(v[0], v[1], v[2]);
+}
+
 }  // namespace
+
+int letterbox_compat_launches() {
+    static const bool two_pass = [] { const char* e = std::getenv("RMR_LETTERBOX_TWO_PASS"); return e && e[0] == '1'; }();
+    return two_pass ? 2 : 1;
+}
 
 // PreParam(cv::Size, cv::Size) — /root/reference/src/detect/preparam.h:46-52, plus the call-site
 // integer geometry of detector.cu:393-410.
@@ -140,8 +178,12 @@ void launch_letterbox(const unsigned char* frame, int stride, const LetterboxGeo
     const dim3 grid((out_w * out_h + 255) / 256, count);
     if (any_clean) letterbox_fused_kernel<<<grid, 256, 0, s>>>(frame, stride, dev_geoms, out, out_w, out_h);
     if (any_unclean) {
-        letterbox_stage_kernel<<<grid, 256, 0, s>>>(frame, stride, dev_geoms, staging, out_w, out_h);
-        letterbox_blob_kernel<<<grid, 256, 0, s>>>(dev_geoms, staging, out, out_w, out_h);
+        if (letterbox_compat_launches() == 2) {
+            letterbox_stage_kernel<<<grid, 256, 0, s>>>(frame, stride, dev_geoms, staging, out_w, out_h);
+            letterbox_blob_kernel<<<grid, 256, 0, s>>>(dev_geoms, staging, out, out_w, out_h);
+        } else {
+            letterbox_compat_kernel<<<grid, 256, 0, s>>>(frame, stride, dev_geoms, staging, out, out_w, out_h);
+        }
     }
     RMR_CUDA(cudaGetLastError());
 }

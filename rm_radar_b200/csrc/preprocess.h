@@ -25,5 +25,7 @@ LetterboxGeom make_letterbox_geom(int src_x, int src_y, int src_w, int src_h, in
 void launch_letterbox(const unsigned char* frame, int stride, const LetterboxGeom* dev_geoms, bool any_unclean,
                       bool any_clean, int count, unsigned char* staging, __half* out, int out_w, int out_h,
                       cudaStream_t s);
+// kernels the compat (staged) path launches per call: 1 fused, 2 with RMR_LETTERBOX_TWO_PASS=1
+int letterbox_compat_launches();
 
 }  // namespace rmr

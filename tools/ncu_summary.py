@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Digest ncu output into the small files kept under profiles/.
 
-  python tools/ncu_summary.py launches <launches.csv> <out.md>      per-kernel totals / shares of one bench step
+  python tools/ncu_summary.py launches <launches.csv> <out.md> [first_kernel]   per-kernel totals / shares of one bench step
+                                                                    (first_kernel: keep from its last launch on = the last whole step)
   python tools/ncu_summary.py full <raw.csv> <out.json> <out.md>    key metrics of an `ncu --set full` capture
                                                                     (raw.csv = `ncu -i rep --page raw --csv`)
 """
@@ -11,13 +12,18 @@ import json
 import sys
 
 
-def launches(path, out_md):
+def launches(path, out_md, first_kernel=None):
     lines = [l for l in open(path) if l.startswith('"')]
     r = csv.reader(lines)
     hdr = next(r)
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
     tot, cnt = collections.Counter(), collections.Counter()
-    for row in r:
+    rows = list(r)
+    if first_kernel:   # keep the last complete step: from the last launch of `first_kernel` to the end
+        starts = [i for i, row in enumerate(rows) if first_kernel in row[ki]]
+        if starts:
+            rows = rows[starts[-1]:]
+    for row in rows:
         name = row[ki].split("(")[0].replace("rmr::<unnamed>::", "").replace("void ", "")
         tot[name] += float(row[vi].replace(",", ""))
         cnt[name] += 1
@@ -75,6 +81,6 @@ def full(path, out_json, out_md):
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
-        launches(sys.argv[2], sys.argv[3])
+        launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
     else:
         full(sys.argv[2], sys.argv[3], sys.argv[4])
