@@ -227,8 +227,9 @@ class Detector {
     Detector() = delete;
     Detector(const Detector&) = delete;
     Detector& operator=(const Detector&) = delete;
-    // `engine_path`: a `.rmeng` plan (python -m rm_radar_b200.engine model.onnx model.rmeng); stands
-    // where the TensorRT `.engine` cache stands (detector.cpp:74-99).  opt_batch_size, input_name and
+    // `engine_path`: `<x>.engine`, `<x>.onnx` or `<x>.rmeng`; the library loads the `<x>.rmeng` plan and, like the
+    // reference with its TensorRT cache (detector.cpp:74-99), builds it from the sibling `<x>.onnx` on first use
+    // (rmr_engine_resolve); neither file -> std::invalid_argument.  opt_batch_size, input_name and
     // opt_level are TensorRT builder knobs: accepted for signature compatibility, unused.
     explicit Detector(std::string_view engine_path, int classes, Size image_size, int max_batch_size,
                       std::optional<int> opt_batch_size = std::nullopt, float nms_thresh = 0.65f,

@@ -291,6 +291,16 @@ int rmr_comm_pack(const rmr_robot_t* robots, int n, int max_robots, float* block
  * tile w, tile h, tile n, bk */
 int rmr_conv_plan(int n, int h_in, int w_in, int cin, int cout, int k, int stride, int* out);
 
+/* ---- engine build (host only, no GPU needed) -------------------------------------------------------------------
+ * Replaces the reference's TensorRT build-and-cache step (/root/reference/src/detect/detector.cpp:74-99 engine path
+ * resolution, :177-243 buildEngineFromONNX, :281-311 serialise).  rmr_engine_build writes the `.rmeng` plan of
+ * `onnx_path` for a network input of input_width x input_height.  rmr_engine_resolve maps the path a caller hands
+ * to Detector (`<x>.engine`, `<x>.onnx` or `<x>.rmeng`) to `<x>.rmeng`, building it from `<x>.onnx` when absent
+ * (RMR_ERR_INVALID_ARGUMENT when neither exists, like the reference's std::invalid_argument), and copies the NUL-terminated
+ * result into out_path (RMR_ERR_CAPACITY if it does not fit).  The detector constructors call it themselves. */
+int rmr_engine_build(const char* onnx_path, const char* engine_path, int input_width, int input_height);
+int rmr_engine_resolve(const char* path, int input_width, int input_height, char* out_path, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

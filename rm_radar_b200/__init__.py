@@ -20,7 +20,7 @@ from . import _lib
 from ._lib import CapacityError, RadarError  # noqa: F401
 
 __all__ = ["Detector", "RobotDetector", "Locator", "Robot", "Detection", "Label", "RadarError", "Comm",
-           "engine_path_for", "run_once", "run_once_records"]
+           "engine_path_for", "build_engine", "run_once", "run_once_records"]
 
 
 class Label(enum.IntEnum):
@@ -76,27 +76,34 @@ class Robot:
         return self.location is not None
 
 
-def engine_path_for(path: str) -> str:
+def build_engine(onnx_path: str, engine_path: str, input_width: int = 640, input_height: int = 640) -> None:
+    """ONNX → `.rmeng` plan through the library's own builder (csrc/engine.cu, `rmr_engine_build`); stands where the
+    reference builds and caches a TensorRT engine (detector.cpp:177-243, 281-311).  Host only."""
+    _lib.check(_lib.load().rmr_engine_build(os.fspath(onnx_path).encode(), os.fspath(engine_path).encode(),
+                                            input_width, input_height))
+
+
+def engine_path_for(path: str, input_width: int = 640, input_height: int = 640) -> str:
     """Resolve the reference's `engine_path` argument.  The reference loads `<x>.engine` or builds it
     from the sibling `<x>.onnx` (detector.cpp:74-99).  We accept `.rmeng`, `.engine` or `.onnx` and
-    build `<x>.rmeng` from `<x>.onnx` when it does not exist yet."""
-    base, ext = os.path.splitext(path)
-    eng = path if ext == ".rmeng" else base + ".rmeng"
-    if os.path.exists(eng):
-        return eng
+    build `<x>.rmeng` from `<x>.onnx` when it does not exist yet (`rmr_engine_resolve`; the C++ constructors
+    do the same on their own).  A read-only model directory falls back to a cache next to the package."""
+    lib = _lib.load()
+    buf = C.create_string_buffer(4096)
+    rc = lib.rmr_engine_resolve(os.fspath(path).encode(), input_width, input_height, buf, len(buf))
+    if rc == 0:
+        return buf.value.decode()
+    if rc == -1:
+        _lib.check(rc)       # ValueError = std::invalid_argument, detector.cpp:80
+    base = os.path.splitext(path)[0]
     onnx = base + ".onnx"
     if not os.path.exists(onnx):
-        raise ValueError(f"neither {eng} nor {onnx} exists")   # std::invalid_argument, detector.cpp:80
-    from . import engine
-    try:
-        engine.build_engine(onnx, eng)
-    except OSError:
-        # read-only model directory: cache next to the package instead
-        cache = os.path.join(os.path.dirname(os.path.abspath(__file__)), "engines")
-        os.makedirs(cache, exist_ok=True)
-        eng = os.path.join(cache, os.path.basename(base) + ".rmeng")
-        if not os.path.exists(eng):
-            engine.build_engine(onnx, eng)
+        _lib.check(rc)
+    cache = os.path.join(os.path.dirname(os.path.abspath(__file__)), "engines")
+    os.makedirs(cache, exist_ok=True)
+    eng = os.path.join(cache, os.path.basename(base) + ".rmeng")
+    if not os.path.exists(eng):
+        build_engine(onnx, eng, input_width, input_height)
     return eng
 
 

@@ -44,7 +44,7 @@ SYMBOLS = [
     "rmr_locator_create", "rmr_locator_destroy", "rmr_locator_update", "rmr_locator_update_device",
     "rmr_locator_cluster", "rmr_locator_search", "rmr_locator_update_pcd", "rmr_pcd_parse", "rmr_locator_load_background", "rmr_locator_set_stream", "rmr_locator_image_size",
     "rmr_locator_read_image", "rmr_locator_stats", "rmr_locator_read_foreground",
-    "rmr_run_once", "rmr_conv_selftest", "rmr_conv_timeline", "rmr_conv_plan", "rmr_postprocess_selftest",
+    "rmr_run_once", "rmr_conv_selftest", "rmr_conv_timeline", "rmr_conv_plan", "rmr_postprocess_selftest", "rmr_engine_build", "rmr_engine_resolve",
     "rmr_comm_unique_id", "rmr_comm_create", "rmr_comm_close", "rmr_comm_destroy", "rmr_comm_publish", "rmr_comm_collect", "rmr_comm_pack",
     "rmr_tracker_create", "rmr_tracker_destroy", "rmr_tracker_update", "rmr_tracker_tracks", "rmr_auction",
     "rmr_jpeg_decoder_create", "rmr_jpeg_decoder_destroy", "rmr_jpeg_decoder_set_stream", "rmr_jpeg_info", "rmr_jpeg_decode",
@@ -142,6 +142,8 @@ def load():
     lib.rmr_run_once.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, ci, ci, ci, P(RobotRec), ci, P(ci)]
     lib.rmr_conv_timeline.argtypes = [ci, ci, ci, ci, ci, ci, ci, vp, ci, P(ci)]
     lib.rmr_conv_plan.argtypes = [ci, ci, ci, ci, ci, ci, ci, P(ci)]
+    lib.rmr_engine_build.argtypes = [C.c_char_p, C.c_char_p, ci, ci]
+    lib.rmr_engine_resolve.argtypes = [C.c_char_p, ci, ci, C.c_char_p, ci]
     lib.rmr_postprocess_selftest.argtypes = [vp, ci, cf, vp, ci, P(ci)]
     lib.rmr_comm_unique_id.argtypes = [vp]
     lib.rmr_comm_create.argtypes = [P(vp), vp, ci, ci, ci, ci]

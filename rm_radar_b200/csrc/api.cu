@@ -6,6 +6,7 @@
 
 #include "../../include/rm_radar_b200.h"
 #include "detector.h"
+#include "engine.h"
 #include "locate.h"
 #include "jpeg.h"
 #include "pcd.h"
@@ -85,6 +86,24 @@ const char* rmr_last_error(void) { return g_last_error.c_str(); }
 
 int rmr_device_count(int* count) {
     return guarded([&] { RMR_CUDA(cudaGetDeviceCount(count)); });
+}
+
+// ---------------------------------------------------------------- engine build (host only)
+int rmr_engine_build(const char* onnx_path, const char* engine_path, int input_width, int input_height) {
+    return guarded([&] {
+        if (!onnx_path || !engine_path) throw std::invalid_argument("null argument");
+        if (input_width <= 0 || input_height <= 0) throw std::invalid_argument("input size must be positive");
+        build_engine(onnx_path, engine_path, input_height, input_width);
+    });
+}
+
+int rmr_engine_resolve(const char* path, int input_width, int input_height, char* out_path, int capacity) {
+    return guarded([&] {
+        if (!path || !out_path || capacity <= 0) throw std::invalid_argument("null argument");
+        const std::string r = resolve_engine(path, input_height, input_width);
+        if (static_cast<int>(r.size()) + 1 > capacity) throw CapacityError("resolved engine path does not fit the buffer");
+        std::memcpy(out_path, r.c_str(), r.size() + 1);
+    });
 }
 
 // ---------------------------------------------------------------- Detector

@@ -1,5 +1,7 @@
 #include "detector.h"
 
+#include "engine.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -68,12 +70,15 @@ Detector::Detector(const std::string& engine_path, int classes, int image_w, int
     : classes_(classes), image_w_(image_w), image_h_(image_h), max_batch_(max_batch), input_w_(input_w),
       input_h_(input_h), device_(device), nms_thresh_(nms_thresh), conf_thresh_(conf_thresh), compat_(compat) {
     if (max_batch <= 0) throw std::invalid_argument("max_batch_size must be positive");
+    // `<x>.engine` / `<x>.onnx` / `<x>.rmeng`: load the plan, building it from the sibling ONNX file when it is not
+    // there yet (detector.cpp:74-99); neither file -> std::invalid_argument before any device work, as there
+    const std::string plan_path = resolve_engine(engine_path, input_h, input_w);
     RMR_CUDA(cudaSetDevice(device_));   // reference: cudaSetDevice(0) hard-coded (detector.cpp:61)
     cudaDeviceProp prop{};
     RMR_CUDA(cudaGetDeviceProperties(&prop, device_));
     if (prop.major != 10)
         throw CudaError(std::string("rm_radar_b200 needs an sm_100a device (B200); found ") + prop.name);
-    net_ = std::make_unique<Net>(engine_path, max_batch);
+    net_ = std::make_unique<Net>(plan_path, max_batch);
     if (net_->in_w() != input_w || net_->in_h() != input_h)
         throw std::invalid_argument("engine input size does not match input_width/input_height");
     if (net_->num_classes() != classes)
