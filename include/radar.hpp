@@ -351,16 +351,18 @@ class RobotDetector {
                            float car_nms_thresh = 0.65f, float car_conf_thresh = 0.25f,
                            float armor_nms_thresh = 0.65f, float armor_conf_thresh = 0.50f, float input_width = 640,
                            float input_height = 640, std::string_view input_name = "images", int input_channels = 3,
-                           int opt_level = 5, bool compat_letterbox = true, int device = 0)
-        : max_cars_(max_cars) {
+                           int opt_level = 5, bool compat_letterbox = true, int device = 0, int frames = 1)
+        : max_cars_(max_cars), frames_(frames) {
         (void)opt_cars; (void)input_name; (void)opt_level;
         if (input_channels != 3) throw std::invalid_argument("input_channels must be 3");
         const std::string car(car_engine_path), armor(armor_engine_path);
-        detail::throw_status(rmr_robot_detector_create(
+        // frames > 1: throughput mode, the detector takes that many images per call (detect(std::vector<ImageView>) /
+        // runBatch) — the batched Detector::detect of the reference (detector.cu:439-502) carried through the cascade
+        detail::throw_status(rmr_robot_detector_create_batched(
             &handle_, car.c_str(), armor.c_str(), image_size.width, image_size.height, armor_classes, max_cars,
             iou_thresh, car_nms_thresh, car_conf_thresh, armor_nms_thresh, armor_conf_thresh,
-            static_cast<int>(input_width), static_cast<int>(input_height), compat_letterbox ? 1 : 0, device));
-        records_.resize(static_cast<size_t>(max_cars));
+            static_cast<int>(input_width), static_cast<int>(input_height), compat_letterbox ? 1 : 0, device, frames));
+        records_.resize(static_cast<size_t>(max_cars) * static_cast<size_t>(frames));
     }
     ~RobotDetector() { rmr_robot_detector_destroy(handle_); }
 
@@ -376,6 +378,22 @@ class RobotDetector {
         for (int i = 0; i < n && i < max_cars_; ++i) robots.push_back(Robot::fromRecord(records_[static_cast<size_t>(i)]));
         return robots;
     }
+    // `n` frames of one size, back to back in memory (frame i at data + i * height * stride): robots per frame
+    std::vector<std::vector<Robot>> detect(const ImageView& first, int n) {
+        if (n < 1 || n > frames_) throw std::invalid_argument("RobotDetector::detect: frame count outside [1, frames]");
+        std::vector<int> counts(static_cast<size_t>(n));
+        const int stride = first.stride_bytes ? first.stride_bytes : first.width * 3;
+        if (rmr_robot_detector_detect_frames(handle_, first.data, 0, n, first.width, first.height, stride, records_.data(),
+                                             max_cars_, counts.data()) != RMR_OK)
+            detail::fatal("RobotDetector::detect(frames)");
+        std::vector<std::vector<Robot>> out(static_cast<size_t>(n));
+        for (int f = 0; f < n; ++f)
+            for (int i = 0; i < counts[static_cast<size_t>(f)] && i < max_cars_; ++i)
+                out[static_cast<size_t>(f)].push_back(Robot::fromRecord(records_[static_cast<size_t>(f) * max_cars_ + i]));
+        return out;
+    }
+    int frames() const noexcept { return frames_; }
+    int maxCars() const noexcept { return max_cars_; }
     // cv::imread + detect: the JPEG is decoded on the device and the frame never crosses PCIe
     std::vector<Robot> detect(JpegDecoder& decoder, const void* file_bytes, size_t size) {
         int n = 0;
@@ -404,7 +422,7 @@ class RobotDetector {
 
    private:
     rmr_robot_detector_t* handle_ = nullptr;
-    int max_cars_ = 0;
+    int max_cars_ = 0, frames_ = 1;
     std::vector<rmr_robot_t> records_;
 };
 
@@ -544,5 +562,73 @@ inline std::vector<Robot> runOnce(RobotDetector& detector, Locator& locator, Tra
     tracker.update(robots, timestamp);
     return robots;
 }
+
+// SampleRadar::runOnce for several camera + LiDAR streams in one call (throughput mode): stream i has its own Locator
+// (background, depth queue); frames of one size back to back (frame i at first.data + i * height * stride), clouds of
+// one size back to back (cloud i at first_cloud.xyz + i * size * stride floats).  Robots per stream.
+inline std::vector<std::vector<Robot>> runBatch(RobotDetector& detector, const std::vector<Locator*>& locators,
+                                                const ImageView& first, const CloudView& first_cloud) {
+    const int n = static_cast<int>(locators.size());
+    if (n < 1 || n > detector.frames()) throw std::invalid_argument("runBatch: stream count outside [1, frames]");
+    std::vector<rmr_locator_t*> handles(locators.size());
+    for (size_t i = 0; i < locators.size(); ++i) {
+        if (!locators[i]) throw std::invalid_argument("runBatch: null locator");
+        handles[i] = locators[i]->handle();
+    }
+    const int cap = detector.maxCars();
+    std::vector<rmr_robot_t> recs(static_cast<size_t>(n) * static_cast<size_t>(cap));
+    std::vector<int> counts(static_cast<size_t>(n));
+    const int stride = first.stride_bytes ? first.stride_bytes : first.width * 3;
+    if (rmr_run_batch(detector.handle(), handles.data(), n, first.data, 0, first.width, first.height, stride,
+                      first_cloud.xyz, 0, first_cloud.size, first_cloud.stride_bytes, recs.data(), cap,
+                      counts.data()) != RMR_OK)
+        detail::fatal("runBatch");
+    std::vector<std::vector<Robot>> out(static_cast<size_t>(n));
+    for (int f = 0; f < n; ++f)
+        for (int i = 0; i < counts[static_cast<size_t>(f)] && i < cap; ++i)
+            out[static_cast<size_t>(f)].push_back(Robot::fromRecord(recs[static_cast<size_t>(f) * cap + i]));
+    return out;
+}
+
+// The multi-GPU exchange (one process per GPU, one camera + LiDAR stream per rank): what SampleRadar would call after
+// runOnce on every GPU.  The reference has no distributed code; the record block is rmr_comm_* 's
+// [valid, label, confidence, is_located, x, y, z, rect area] per robot.  Rank 0 makes the id (Exchange::uniqueId) and
+// the host program hands it to the other ranks (MPI, a socket, torch.distributed in bench.py).
+class Exchange {
+   public:
+    using Id = std::array<uint8_t, RMR_COMM_ID_BYTES>;
+    static Id uniqueId() {
+        Id id{};
+        detail::throw_status(rmr_comm_unique_id(id.data()));
+        return id;
+    }
+    Exchange(const Exchange&) = delete;
+    Exchange& operator=(const Exchange&) = delete;
+    Exchange(const Id& id, int rank, int world, int device = 0, int max_robots = 20)
+        : world_(world), max_robots_(max_robots) {
+        detail::throw_status(rmr_comm_create(&handle_, id.data(), rank, world, device, max_robots));
+    }
+    ~Exchange() { rmr_comm_destroy(handle_); }
+    // enqueue this rank's robots for the all-gather and return at once (it overlaps the next frame)
+    void publish(const std::vector<Robot>& robots) {
+        records_.resize(robots.size());
+        for (size_t i = 0; i < robots.size(); ++i) robots[i].toFullRecord(records_[i]);
+        if (rmr_comm_publish(handle_, records_.data(), static_cast<int>(robots.size()), nullptr) != RMR_OK)
+            detail::fatal("Exchange::publish");
+    }
+    // wait for the last publish: [world][max_robots][RMR_RECORD_FLOATS]
+    std::vector<float> collect() {
+        std::vector<float> all(static_cast<size_t>(world_) * static_cast<size_t>(max_robots_) * RMR_RECORD_FLOATS);
+        if (rmr_comm_collect(handle_, all.data()) != RMR_OK) detail::fatal("Exchange::collect");
+        return all;
+    }
+    // orderly collective shutdown: every rank, at the same point of the program
+    void close() { detail::throw_status(rmr_comm_close(handle_)); }
+
+   private:
+    rmr_comm_t* handle_ = nullptr;
+    int world_ = 1, max_robots_ = 20;
+    std::vector<rmr_robot_t> records_;
+};
 
 }  // namespace radar

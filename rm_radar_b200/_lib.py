@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librm_radar_b200.so")
+# RMR_LIB_PATH: another build of the same library (A/B timing of two kernel versions on one GPU box); default in-tree
+LIB_PATH = os.environ.get("RMR_LIB_PATH") or os.path.join(HERE, "librm_radar_b200.so")
 MAX_ARMORS = 16
 
 

@@ -1,5 +1,7 @@
 // extern "C" boundary (include/rm_radar_b200.h).  Exceptions become status codes + a thread-local
 // message; nothing here computes on the CPU.
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <random>
@@ -628,6 +630,11 @@ int rmr_run_once(rmr_robot_detector_t* d, rmr_locator_t* l, const void* frame, i
     return guarded([&] {
         if (!d || !l || !out || !count) throw std::invalid_argument("null argument");
         if (xyz && (point_stride_bytes % 4 != 0 || point_stride_bytes < 12)) throw std::invalid_argument("bad point stride");
+        // RMR_TRACE=1: host wall-clock of the stages of this call on stderr (us since entry), for tuning only
+        static const bool trace = [] { const char* e = std::getenv("RMR_TRACE"); return e && e[0] == '1'; }();
+        const auto t0 = std::chrono::steady_clock::now();
+        double t_us[5] = {0, 0, 0, 0, 0};
+        auto stamp = [&](int i) { if (trace) t_us[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
         // 1. car stage goes out first (upload + letterbox + network + decode/NMS + D2H), nothing waits
         d->impl->begin(static_cast<const uint8_t*>(frame), frame_on_device != 0, width, height, stride_bytes);
         // 2. the locator's launches are issued while the car network runs (its own stream)
@@ -635,27 +642,51 @@ int rmr_run_once(rmr_robot_detector_t* d, rmr_locator_t* l, const void* frame, i
         if (cloud_on_device) l->impl->update_device(static_cast<const float*>(xyz), n_points, point_stride_bytes / 4, l->stream);
         else l->impl->update_host(static_cast<const float*>(xyz), n_points, point_stride_bytes / 4, l->stream);
         l->impl->cluster(l->stream);
-        // 3. car results -> armor stage -> robots
+        stamp(0);
+        // 3. car boxes -> armor stage enqueued.  A robot's rectangle is the box of the car it is made from
+        //    (Robot::setDetection, robot.cpp:41-74) and Locator::search treats every rectangle on its own
+        //    (locate.cpp:276-326), so the search of all car boxes runs beside the armor network instead of after it
+        const std::vector<Detection>& cars = d->impl->cars();
+        stamp(1);
+        const int n_cars = static_cast<int>(cars.size());
+        std::vector<LocResult> res(n_cars);
+        const bool early = n_cars > 0 && n_cars <= l->impl->max_robots();
+        if (early) {
+            std::vector<RectF> rects(n_cars);
+            for (int i = 0; i < n_cars; ++i) rects[i] = RectF{cars[i].x, cars[i].y, cars[i].width, cars[i].height, 1};
+            l->impl->search_begin(rects.data(), n_cars, l->stream);
+        }
+        // 4. armors -> robots (label vote, de-duplication)
+        stamp(2);
         auto robots = d->impl->finish();
+        stamp(3);
         *count = static_cast<int>(robots.size());
         const int n = std::min<int>(*count, capacity);
         for (int i = 0; i < n; ++i) fill_robot(robots[i], out + i);
-        // 4. Locator::search on the records
-        if (n > 0) {
+        // 5. Locator::search results onto the records
+        if (early) {
+            l->impl->search_end(res.data(), n_cars, l->stream);
+        } else if (n > 0) {     // more cars than the locator's search capacity: search the robots that are left
             std::vector<RectF> rects(n);
-            std::vector<LocResult> res(n);
             for (int i = 0; i < n; ++i)
                 rects[i] = RectF{out[i].rect[0], out[i].rect[1], out[i].rect[2], out[i].rect[3], out[i].has_rect};
+            res.resize(n);
             l->impl->search(rects.data(), res.data(), n, l->stream);
-            for (int i = 0; i < n; ++i) {
-                if (!res[i].located) continue;
-                out[i].is_located = 1;
-                out[i].location[0] = res[i].x; out[i].location[1] = res[i].y; out[i].location[2] = res[i].z;
-                out[i].cluster = res[i].cluster;
-                out[i].cluster_points = res[i].npoints;
-            }
         } else {
             RMR_CUDA(cudaStreamSynchronize(l->stream));
+        }
+        stamp(4);
+        if (trace)
+            std::fprintf(stderr, "rmr_run_once us: enqueued %.1f | cars+armor enqueued %.1f | search enqueued %.1f | armor done %.1f | "
+                         "search done %.1f | device car %.1f armor %.1f\n", t_us[0], t_us[1], t_us[2], t_us[3], t_us[4],
+                         d->impl->last_car_ms() * 1e3, d->impl->last_armor_ms() * 1e3);
+        for (int i = 0; i < n; ++i) {
+            const LocResult& r = res[early ? robots[i].car : i];
+            if (!r.located) continue;
+            out[i].is_located = 1;
+            out[i].location[0] = r.x; out[i].location[1] = r.y; out[i].location[2] = r.z;
+            out[i].cluster = r.cluster;
+            out[i].cluster_points = r.npoints;
         }
     });
 }
@@ -681,35 +712,48 @@ int rmr_run_batch(rmr_robot_detector_t* d, rmr_locator_t* const* locators, int n
             else l->impl->update_host(cloud, n_points, point_stride_bytes / 4, l->stream);
             l->impl->cluster(l->stream);
         }
-        // 3. car results -> armor stage over all ROIs -> robots per frame
+        // 3. car boxes of every frame; each stream's search of them runs beside the armor stage (see rmr_run_once)
+        const std::vector<std::vector<Detection>>& cars = d->impl->batch_cars();
+        std::vector<char> early(n_frames, 0);
+        for (int f = 0; f < n_frames; ++f) {
+            const int nc = static_cast<int>(cars[f].size());
+            if (nc == 0 || nc > locators[f]->impl->max_robots()) continue;
+            std::vector<RectF> rects(nc);
+            for (int i = 0; i < nc; ++i) rects[i] = RectF{cars[f][i].x, cars[f][i].y, cars[f][i].width, cars[f][i].height, 1};
+            locators[f]->impl->search_begin(rects.data(), nc, locators[f]->stream);
+            early[f] = 1;
+        }
+        // 4. armor stage over all ROIs -> robots per frame
         auto robots = d->impl->finish_batch();
-        // 4. Locator::search per stream: all launches first, then the waits
-        std::vector<std::vector<RectF>> rects(n_frames);
+        const std::vector<std::vector<Detection>>& cars_done = d->impl->last_batch_cars();
+        // 5. search results onto the records (late search only where a frame has more cars than the locator takes)
+        std::vector<LocResult> res;
         for (int f = 0; f < n_frames; ++f) {
             counts[f] = static_cast<int>(robots[f].size());
             const int n = std::min<int>(counts[f], capacity);
             rmr_robot_t* o = out + static_cast<size_t>(f) * capacity;
-            rects[f].resize(n);
-            for (int i = 0; i < n; ++i) {
-                fill_robot(robots[f][i], o + i);
-                rects[f][i] = RectF{o[i].rect[0], o[i].rect[1], o[i].rect[2], o[i].rect[3], o[i].has_rect};
-            }
-            if (n > 0) locators[f]->impl->search_begin(rects[f].data(), n, locators[f]->stream);
-        }
-        std::vector<LocResult> res;
-        for (int f = 0; f < n_frames; ++f) {
-            const int n = static_cast<int>(rects[f].size());
+            for (int i = 0; i < n; ++i) fill_robot(robots[f][i], o + i);
             rmr_locator_t* l = locators[f];
-            if (n == 0) { RMR_CUDA(cudaStreamSynchronize(l->stream)); continue; }
-            res.resize(n);
-            l->impl->search_end(res.data(), n, l->stream);
-            rmr_robot_t* o = out + static_cast<size_t>(f) * capacity;
+            const int nc = static_cast<int>(cars_done[f].size());
+            if (early[f]) {
+                res.resize(nc);
+                l->impl->search_end(res.data(), nc, l->stream);
+            } else if (n > 0) {
+                std::vector<RectF> rects(n);
+                for (int i = 0; i < n; ++i) rects[i] = RectF{o[i].rect[0], o[i].rect[1], o[i].rect[2], o[i].rect[3], o[i].has_rect};
+                res.resize(n);
+                l->impl->search(rects.data(), res.data(), n, l->stream);
+            } else {
+                RMR_CUDA(cudaStreamSynchronize(l->stream));
+                continue;
+            }
             for (int i = 0; i < n; ++i) {
-                if (!res[i].located) continue;
+                const LocResult& r = res[early[f] ? robots[f][i].car : i];
+                if (!r.located) continue;
                 o[i].is_located = 1;
-                o[i].location[0] = res[i].x; o[i].location[1] = res[i].y; o[i].location[2] = res[i].z;
-                o[i].cluster = res[i].cluster;
-                o[i].cluster_points = res[i].npoints;
+                o[i].location[0] = r.x; o[i].location[1] = r.y; o[i].location[2] = r.z;
+                o[i].cluster = r.cluster;
+                o[i].cluster_points = r.npoints;
             }
         }
     });

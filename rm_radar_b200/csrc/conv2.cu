@@ -85,7 +85,30 @@ struct DupMaps {
 };
 
 // kHalo: 3x3 stride-1 layers, one [18][pw] pixel patch per channel chunk serves the nine taps.
-template <bool kHalo, bool kRes>
+// (tile_w, tile_h, tile_n) of m-tile j0, j0 + gm, j0 + 2 gm, ... without a division per tile: the step is decomposed
+// once and added with carries (a 32-bit division by a run-time value is ~100 cycles; four of them per tile were
+// a third of an epilogue-bound tile, profiles/r2_timeline_epi.txt)
+struct TileWalk {
+    int w, h, n, gw, gh, gn, tiles_w, tiles_h;
+    // (gw, gh, gn) = the step gm in tile coordinates, decomposed on the host (Conv2Params::gm_w/h/n)
+    __device__ __forceinline__ TileWalk(int j0, const Conv2Params& p) : gw(p.gm_w), gh(p.gm_h), gn(p.gm_n), tiles_w(p.tiles_w), tiles_h(p.tiles_h) {
+        w = j0 % tiles_w; const int t = j0 / tiles_w; h = t % tiles_h; n = t / tiles_h;
+    }
+    __device__ __forceinline__ void next() {
+        w += gw;
+        int c = w >= tiles_w ? 1 : 0;
+        w -= c * tiles_w;
+        h += gh + c;
+        c = h >= tiles_h ? 1 : 0;
+        h -= c * tiles_h;
+        n += gn + c;
+    }
+};
+
+// kDbg: the instrumented build behind rmr_conv_timeline.  The stamps are compiled out of the product kernel: clock64()
+// is a scheduling barrier even when predicated off, and a dozen of them in the epilogue cost 12 us (car) + 22 us (armor,
+// 7 ROIs) per frame (profiles/r2_summary.md, "debug stamps").
+template <bool kHalo, bool kRes, bool kDbg>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
              const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
@@ -107,7 +130,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     // profiling aid: slot 0 start, 1 setup done, 2 + 8 t + {0: A producer past its empty wait, 1: issuer past the
     // accumulator wait, 2: first operands seen, 3: all MMAs of the tile issued, 4: epilogue sees the accumulator,
     // 5: accumulator read out, 6: first epilogue group stored, 7: second group stored} for tiles t < 7, 60 exit
-    long long* dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 64 : nullptr;
+    long long* dbg = (kDbg && p.dbg) ? p.dbg + static_cast<size_t>(blockIdx.x) * 64 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
     // this CTA's slice: output channels [ch0, ch0 + block_n), pixel tiles j0, j0 + gm, ...
@@ -206,12 +229,9 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 pdl_wait2();   // activations are the previous layer's output
                 uint32_t aoff = 0, adst = a_ring, phase = 0;
                 int ti = 0;
+                TileWalk tile(j0, p);
                 for (int mt = j0; mt < p.m_tiles; mt += p.gm, ++ti) {
-                    int t = mt;
-                    const int tile_w = t % p.tiles_w; t /= p.tiles_w;
-                    const int tile_h = t % p.tiles_h;
-                    const int tile_n = t / p.tiles_h;
-                    const int ow0 = tile_w * p.tw, oh0 = tile_h * p.th, n0 = tile_n * p.tn;
+                    const int ow0 = tile.w * p.tw, oh0 = tile.h * p.th, n0 = tile.n * p.tn;
                     int cx = p.cin_coff;
                     for (int c = 0; c < kpt; ++c, cx += bk) {
                         mbar_wait_spin(aempty0 + aoff, phase ^ 1u);
@@ -224,6 +244,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                         aoff += 8u; adst += a_stage;
                         if (aoff == aend) { aoff = 0; adst = a_ring; phase ^= 1u; }
                     }
+                    if (mt + p.gm < p.m_tiles) tile.next();   // after this tile's loads are on their way
                 }
             } else if (!p.b_resident) {
                 // streamed weights, three taps (one kernel row) per stage; k-block of (tap, chunk c) = tap * kpt + c
@@ -259,18 +280,20 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             if (is_a) pdl_wait2();   // activations are the previous layer's output
             uint32_t aoff = 0, adst = a_ring, phase = 0;
             int ti = 0;
+            TileWalk tile(j0, p);
             for (int mt = j0; mt < p.m_tiles; mt += p.gm, ++ti) {
-                int t = mt;
-                const int tile_w = t % p.tiles_w; t /= p.tiles_w;
-                const int tile_h = t % p.tiles_h;
-                const int tile_n = t / p.tiles_h;
-                const int ow0 = tile_w * p.tw, oh0 = tile_h * p.th, n0 = tile_n * p.tn;
+                const int ow0 = tile.w * p.tw, oh0 = tile.h * p.th, n0 = tile.n * p.tn;
                 int tap = 0, kc = 0;
                 int4 tp = s_tap[0];
                 int cx = p.cin_coff + tp.x;
                 for (int u = 0; u < nunits; u += g) {
                     const int gg = min(g, nunits - u);
-                    mbar_wait_spin(aempty0 + aoff, phase ^ 1u);
+                    // warp 1 waits only for stages it puts something into (the weight box of a joint stage, the odd
+                    // activation boxes).  A warp that only watches a barrier can miss a whole phase — the parity wait
+                    // then never catches up and the warp is still waiting when the CTA is done (a hang at the end of
+                    // the tile loop, seen once the debug stamps no longer slowed warp 0 down).  A stage that needs a
+                    // box of warp 1 cannot complete twice without it, so its own waits never alias.
+                    if (is_a || p.joint || gg > 1) mbar_wait_spin(aempty0 + aoff, phase ^ 1u);
                     if (dbg && leader && is_a && u == 0 && ti < 7 && !p.dbg_mode) dbg[2 + 8 * ti] = clock64();
                     if (leader) {
                         if (is_a) mbar_expect_tx(afull0 + aoff, static_cast<uint32_t>(gg) * a_kb + stage_tx_b);
@@ -295,6 +318,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     aoff += 8u; adst += a_stage;
                     if (aoff == aend) { aoff = 0; adst = a_ring; phase ^= 1u; }
                 }
+                if (mt + p.gm < p.m_tiles) tile.next();   // after this tile's loads are on their way
             }
         }
     } else if (warp == 2) {
@@ -343,14 +367,14 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             const uint32_t ab = it & 1u;
             mbar_wait_spin(accempty0 + 8u * ab, ((it >> 1) & 1u) ^ 1u);
             tc_fence_after();
-            if (dbg && leader && it < 7) dbg[3 + 8 * it] = clock64();
+            if (dbg && leader && it < 7 && p.dbg_mode != 2) dbg[3 + 8 * it] = clock64();
             const uint32_t acc = tmem_base + ab * p.acc_stride;
             uint32_t accumulate = 0;
             if (resident) b_lo = b_lo0;   // resident weights: slot = k-block index
             if (kHalo) {
                 for (int c = u0; c < u1; ++c) {
                     mbar_wait_spin(afull0 + aoff, aphase);
-                    if (dbg && leader && c == u0 && it < 7) dbg[4 + 8 * it] = clock64();
+                    if (dbg && leader && c == u0 && it < 7 && p.dbg_mode != 2) dbg[4 + 8 * it] = clock64();
                     if (resident) {
                         // nine k-blocks of MMAs and nothing else; the weight tile of (tap, chunk c) is k-block tap * kpt + c
                         if (leader) {
@@ -401,7 +425,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 for (int u = u0; u < u1; u += g) {
                     const int gg = min(g, u1 - u);
                     mbar_wait_spin(afull0 + aoff, aphase);
-                    if (dbg && leader && u == u0 && it < 7) dbg[4 + 8 * it] = clock64();
+                    if (dbg && leader && u == u0 && it < 7 && p.dbg_mode != 2) dbg[4 + 8 * it] = clock64();
                     if (leader) {
                         uint32_t alo = a_lo, blo = resident ? b_lo : a_lo + b_in_stage;
                         for (int j = 0; j < gg; ++j) {
@@ -421,7 +445,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 }
             }
             if (leader) umma_commit(accfull0 + 8u * ab);   // accumulator of this tile complete
-            if (dbg && leader && it < 7) dbg[5 + 8 * it] = clock64();
+            if (dbg && leader && it < 7 && p.dbg_mode != 2) dbg[5 + 8 * it] = clock64();
             __syncwarp();
         }
     } else if (warp == 3) {
@@ -437,16 +461,9 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             const uint32_t outready0 = smem_u32(&bar_outready[0]), stfree0 = smem_u32(&bar_stfree[0]), resfull0 = smem_u32(&bar_resfull[0]);
             const uint32_t res_bytes = 128u * 64u;   // [128 rows][32 fp16]
             pdl_wait2();   // shortcut reads and output writes must follow the previous grid
-            auto coords = [&](int mt, int& ow0, int& oh0, int& n0) {
-                int t = mt;
-                const int tile_w = t % p.tiles_w; t /= p.tiles_w;
-                const int tile_h = t % p.tiles_h;
-                const int tile_n = t / p.tiles_h;
-                ow0 = tile_w * p.tw; oh0 = tile_h * p.th; n0 = tile_n * p.tn;
-            };
-            int ow0, oh0, n0;
+            TileWalk tile(j0, p);
+            int ow0 = tile.w * p.tw, oh0 = tile.h * p.th, n0 = tile.n * p.tn;
             if (has_res && j0 < p.m_tiles) {
-                coords(j0, ow0, oh0, n0);
                 if (leader)
                     for (int sidx = 0; sidx < p.nchunks; ++sidx) {
                         mbar_expect_tx(resfull0 + 8u * sidx, res_bytes);
@@ -456,12 +473,12 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             }
             uint32_t it = 0;
             for (int mt = j0; mt < p.m_tiles; mt += p.gm, ++it) {
-                coords(mt, ow0, oh0, n0);
-                int nw0 = 0, nh0 = 0, nn0 = 0;
                 const bool more = mt + p.gm < p.m_tiles;
-                if (more) coords(mt + p.gm, nw0, nh0, nn0);
+                if (more) tile.next();   // the tile after this one: its shortcut is fetched as soon as a sub-tile is free
+                const int nw0 = tile.w * p.tw, nh0 = tile.h * p.th, nn0 = tile.n * p.tn;
                 for (int sidx = 0; sidx < p.nchunks; ++sidx) {
                     mbar_wait_spin(outready0 + 8u * sidx, it & 1u);
+                    if (dbg && leader && sidx == 0 && it < 7 && p.dbg_mode == 2) dbg[9 + 8 * it] = clock64();
                     if (leader) {
                         const uint32_t src = stage + sidx * p.sub_bytes;
                         tma_store_4d(&tm_out, src, p.out_coff + ch0 + 32 * sidx, ow0, oh0, n0);
@@ -486,6 +503,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     }
                     __syncwarp();
                 }
+                ow0 = nw0; oh0 = nh0; n0 = nn0;
             }
             if (leader) bulk_wait_all();   // the global writes are complete before the CTA retires
             __syncwarp();
@@ -504,14 +522,22 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         if (!p.tma_epi) pdl_wait2();   // residual reads and output writes must follow the previous grid
         uint32_t it = 0;
         for (int mt = j0; mt < p.m_tiles; mt += p.gm, ++it) {
-            int t = mt;
-            const int tile_w = t % p.tiles_w; t /= p.tiles_w;
-            const int tile_h = t % p.tiles_h;
-            const int tile_n = t / p.tiles_h;
-            const int ow = tile_w * p.tw + tw_i, oh = tile_h * p.th + th_i, n = tile_n * p.tn + tn_i;
-            const bool valid = (ow < p.w_out) && (oh < p.h_out) && (n < p.n);
-            const size_t pix = (static_cast<size_t>(n) * p.h_out + oh) * p.w_out + ow;
-            const __half* rptr = (kRes && p.res != nullptr && valid) ? p.res + pix * p.res_pitch + p.res_coff + ch0 : nullptr;
+            // pixel of this thread's row: only the direct-store epilogue addresses global memory itself (four integer
+            // divisions per tile — ~500 cycles the TMA epilogue, whose tiles are addressed by warp 3, must not pay)
+            int ow = 0, oh = 0, n = 0;
+            bool valid = false;
+            size_t pix = 0;
+            const __half* rptr = nullptr;
+            if (!p.tma_epi) {
+                int t = mt;
+                const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+                const int tile_h = t % p.tiles_h;
+                const int tile_n = t / p.tiles_h;
+                ow = tile_w * p.tw + tw_i; oh = tile_h * p.th + th_i; n = tile_n * p.tn + tn_i;
+                valid = (ow < p.w_out) && (oh < p.h_out) && (n < p.n);
+                pix = (static_cast<size_t>(n) * p.h_out + oh) * p.w_out + ow;
+                rptr = (kRes && p.res != nullptr && valid) ? p.res + pix * p.res_pitch + p.res_coff + ch0 : nullptr;
+            }
             const uint32_t ab = it & 1u;
             const uint32_t taddr = tmem_base + ab * p.acc_stride + lane_addr;
 
@@ -619,9 +645,12 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 }
             };
 
+            const bool fine = dbg && threadIdx.x == 128 && it < 7 && p.dbg_mode == 2;   // epilogue steps of warp 4
+            if (fine) dbg[2 + 8 * it] = clock64();
             mbar_wait_spin(smem_u32(&bar_accfull[ab]), (it >> 1) & 1);
             tc_fence_after();
             if (dbg && threadIdx.x == 128 && it < 7 && !p.dbg_mode) dbg[6 + 8 * it] = clock64();
+            if (fine) dbg[3 + 8 * it] = clock64();
             // the last chunk this warp reads: once it is in registers the accumulator goes back to the issuer
             int last_c0 = -1;
             for (int c0 = chunk0; c0 < nvalid; c0 += 64) last_c0 = c0;
@@ -640,6 +669,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     __syncwarp();
                     tmem_ld_32(taddr + c0, v);
                     tmem_ld_wait();
+                    if (fine && c0 == chunk0) dbg[4 + 8 * it] = clock64();
                     if (c0 == last_c0) {
                         tc_fence_before();
                         __syncwarp();
@@ -681,8 +711,10 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                             }
                         }
                     } else {
+                        if (fine && c0 == chunk0) dbg[5 + 8 * it] = clock64();
                         mbar_wait_spin(smem_u32(&bar_stfree[sidx]), (it & 1u) ^ 1u);   // the previous tile's store has read it out
                     }
+                    if (fine && c0 == chunk0) dbg[6 + 8 * it] = clock64();
                     if (f32out) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
@@ -701,8 +733,10 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                                          "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
                         }
                     }
+                    if (fine && c0 == chunk0) dbg[7 + 8 * it] = clock64();
                     fence_proxy_async();   // generic-proxy writes -> visible to the bulk store
                     mbar_arrive(smem_u32(&bar_outready[sidx]));
+                    if (fine && c0 == chunk0) dbg[8 + 8 * it] = clock64();
                 }
                 if (dbg && it < 7 && !p.dbg_mode) {
                     if (threadIdx.x == 128) dbg[8 + 8 * it] = clock64();
@@ -918,6 +952,9 @@ void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
     p.units_per_split = (units + p.splits - 1) / p.splits;
     p.ns_total = p.n_tiles * p.splits;
     p.gm = static_cast<int>(std::max<long>(1, std::min<long>(p.m_tiles, kSM / std::max(1, std::min(p.ns_total, kSM)))));
+    p.gm_w = p.gm % p.tiles_w;
+    p.gm_h = (p.gm / p.tiles_w) % p.tiles_h;
+    p.gm_n = p.gm / p.tiles_w / p.tiles_h;
     const int kb_cta = p.units_per_split * kb_per_unit;
 
     // ---- shared-memory layout: [A (or joint) ring][weights: resident slice | halo stream ring][epilogue staging] ----
@@ -1097,10 +1134,14 @@ void conv2_init() {
             RMR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
             RMR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         };
-        prep(conv2_kernel<false, false>);
-        prep(conv2_kernel<false, true>);
-        prep(conv2_kernel<true, false>);
-        prep(conv2_kernel<true, true>);
+        prep(conv2_kernel<false, false, false>);
+        prep(conv2_kernel<false, true, false>);
+        prep(conv2_kernel<true, false, false>);
+        prep(conv2_kernel<true, true, false>);
+        prep(conv2_kernel<false, false, true>);
+        prep(conv2_kernel<false, true, true>);
+        prep(conv2_kernel<true, false, true>);
+        prep(conv2_kernel<true, true, true>);
         encode_fn2();
     });
 }
@@ -1125,12 +1166,13 @@ void launch_conv2(const ConvLaunch& l, cudaStream_t s, bool pdl) {
     const bool res = l.q.res != nullptr;
     DupMaps dm;
     std::memcpy(dm.m, l.tm_dup, sizeof(dm.m));
-    if (l.q.halo) {
-        if (res) RMR_CUDA((cudaLaunchKernelEx(&cfg, conv2_kernel<true, true>, l.tm_a, l.tm_b, l.tm_out, l.tm_res, dm, l.q)));
-        else RMR_CUDA((cudaLaunchKernelEx(&cfg, conv2_kernel<true, false>, l.tm_a, l.tm_b, l.tm_out, l.tm_res, dm, l.q)));
+    auto go = [&](auto kernel) { RMR_CUDA((cudaLaunchKernelEx(&cfg, kernel, l.tm_a, l.tm_b, l.tm_out, l.tm_res, dm, l.q))); };
+    if (l.q.dbg) {      // instrumented build (rmr_conv_timeline only)
+        if (l.q.halo) { if (res) go(conv2_kernel<true, true, true>); else go(conv2_kernel<true, false, true>); }
+        else { if (res) go(conv2_kernel<false, true, true>); else go(conv2_kernel<false, false, true>); }
     } else {
-        if (res) RMR_CUDA((cudaLaunchKernelEx(&cfg, conv2_kernel<false, true>, l.tm_a, l.tm_b, l.tm_out, l.tm_res, dm, l.q)));
-        else RMR_CUDA((cudaLaunchKernelEx(&cfg, conv2_kernel<false, false>, l.tm_a, l.tm_b, l.tm_out, l.tm_res, dm, l.q)));
+        if (l.q.halo) { if (res) go(conv2_kernel<true, true, false>); else go(conv2_kernel<true, false, false>); }
+        else { if (res) go(conv2_kernel<false, true, false>); else go(conv2_kernel<false, false, false>); }
     }
 }
 

@@ -145,7 +145,12 @@ void Detector::enqueue(const uint8_t* dev_frame, int stride, const Roi* rois, in
         if (force_stage) pinned_geoms_[i].clean = 0;
         (pinned_geoms_[i].clean ? any_clean : any_unclean) = true;
     }
-    RMR_CUDA(cudaMemcpyAsync(dev_geoms_, pinned_geoms_, sizeof(LetterboxGeom) * n, cudaMemcpyHostToDevice, stream_));
+    // same geometry as the last call (the car stage: one full frame of a fixed size): the device copy is still right
+    if (uploaded_geoms_.size() != static_cast<size_t>(n) ||
+        std::memcmp(uploaded_geoms_.data(), pinned_geoms_, sizeof(LetterboxGeom) * n) != 0) {
+        RMR_CUDA(cudaMemcpyAsync(dev_geoms_, pinned_geoms_, sizeof(LetterboxGeom) * n, cudaMemcpyHostToDevice, stream_));
+        uploaded_geoms_.assign(pinned_geoms_, pinned_geoms_ + n);
+    }
     launch_letterbox(dev_frame, stride, dev_geoms_, any_unclean, any_clean, n, staging_, net_->input(), input_w_,
                      input_h_, stream_);
     RMR_CUDA(cudaEventRecord(ev_fwd0_, stream_));
@@ -359,6 +364,7 @@ void RobotDetector::begin(const uint8_t* frame, bool on_device, int w, int h, in
         dev_stride = w * 3;
     }
     cur_frame_ = dev; cur_w_ = w; cur_h_ = h; cur_stride_ = dev_stride;
+    mid_done_ = false;
     const Roi full{0, 0, w, h};
     car_->enqueue(dev, dev_stride, &full, 1);
 }
@@ -373,12 +379,18 @@ std::vector<RobotRecord> RobotDetector::detect_device(const uint8_t* dev_bgr, in
     return finish();
 }
 
-std::vector<RobotRecord> RobotDetector::finish() {
+const std::vector<Detection>& RobotDetector::cars() {
     const uint8_t* dev_bgr = cur_frame_;
     const int stride = cur_stride_;
     if (dev_bgr == nullptr) throw std::invalid_argument("RobotDetector::finish without begin");
-    cur_frame_ = nullptr;
-    std::vector<Detection> cars = car_->collect()[0];
+    if (mid_done_) return last_cars_;
+    std::vector<Detection> cars;
+    try {
+        cars = std::move(car_->collect()[0]);
+    } catch (...) {
+        cur_frame_ = nullptr;      // the frame is over: the next call starts with begin()
+        throw;
+    }
     last_launches_ = car_->last_launches();
     last_flops_ = car_->net().flops_per_image();
     last_car_ms_ = car_->last_forward_ms();
@@ -388,26 +400,34 @@ std::vector<RobotRecord> RobotDetector::finish() {
     // cv::Rect(float, float, float, float): truncation (detector.cpp:420-421); ROIs are read from the
     // resident frame instead of `image(rect).clone()`
     std::vector<Roi> rois;
-    std::vector<int> roi_of_car(cars.size(), -1);
+    roi_of_car_.assign(cars.size(), -1);
     for (size_t i = 0; i < cars.size(); ++i) {
         Roi r{static_cast<int>(cars[i].x), static_cast<int>(cars[i].y), static_cast<int>(cars[i].width),
               static_cast<int>(cars[i].height)};
         if (r.w <= 0 || r.h <= 0) continue;   // cv::Mat ROI of zero area: nothing to detect in
-        roi_of_car[i] = static_cast<int>(rois.size());
+        roi_of_car_[i] = static_cast<int>(rois.size());
         rois.push_back(r);
     }
-    std::vector<std::vector<Detection>> armor_batch;
     if (!rois.empty()) {
-        armor_batch = armor_->detect_device_rois(dev_bgr, stride, rois.data(), static_cast<int>(rois.size()));
+        armor_->enqueue(dev_bgr, stride, rois.data(), static_cast<int>(rois.size()));
         last_launches_ += armor_->last_launches();
-        last_armor_ms_ = armor_->last_forward_ms();
         last_flops_ += armor_->net().flops_per_image() * rois.size();
     }
-    last_cars_ = cars;
-    last_armors_.assign(cars.size(), {});
-    for (size_t i = 0; i < cars.size(); ++i)
-        if (roi_of_car[i] >= 0) last_armors_[i] = armor_batch[roi_of_car[i]];
-    return assemble(cars, last_armors_);
+    last_cars_ = std::move(cars);
+    mid_done_ = true;
+    return last_cars_;
+}
+
+std::vector<RobotRecord> RobotDetector::finish() {
+    cars();
+    cur_frame_ = nullptr;
+    mid_done_ = false;
+    std::vector<std::vector<Detection>> armor_batch = armor_->collect();   // empty when nothing was enqueued
+    if (!armor_batch.empty()) last_armor_ms_ = armor_->last_forward_ms();
+    last_armors_.assign(last_cars_.size(), {});
+    for (size_t i = 0; i < last_cars_.size(); ++i)
+        if (roi_of_car_[i] >= 0) last_armors_[i] = armor_batch[roi_of_car_[i]];
+    return assemble(last_cars_, last_armors_);
 }
 
 // Robot::setDetection per car, then the label de-duplication of RobotDetector::detect (detector.cpp:426-455)
@@ -418,6 +438,7 @@ std::vector<RobotRecord> RobotDetector::assemble(const std::vector<Detection>& c
     std::map<int, RobotRecord> by_label;
     for (size_t i = 0; i < cars.size(); ++i) {
         RobotRecord robot = set_detection(cars[i], armors[i]);
+        robot.car = static_cast<int>(i);
         if (!robot.detected) {
             robots.push_back(robot);
             continue;
@@ -450,40 +471,64 @@ void RobotDetector::begin_batch(const uint8_t* frames, bool on_device, int n, in
         dev = buf;
     }
     cur_frame_ = dev; cur_w_ = w; cur_h_ = h; cur_stride_ = stride; cur_n_ = n;
+    mid_done_ = false;
     std::vector<Roi> full(n);
     for (int i = 0; i < n; ++i) full[i] = Roi{0, i * h, w, h};   // the batch is one tall strip of rows
     car_->enqueue(dev, stride, full.data(), n);
 }
 
-std::vector<std::vector<RobotRecord>> RobotDetector::finish_batch() {
+const std::vector<std::vector<Detection>>& RobotDetector::batch_cars() {
     if (cur_frame_ == nullptr) throw std::invalid_argument("RobotDetector::finish_batch without begin_batch");
-    const uint8_t* dev = cur_frame_;
-    const int n = cur_n_, h = cur_h_, stride = cur_stride_;
-    cur_frame_ = nullptr;
-    std::vector<std::vector<Detection>> cars = car_->collect();
+    if (mid_done_) return batch_cars_;
+    const int n = cur_n_, h = cur_h_;
+    try {
+        batch_cars_ = car_->collect();
+    } catch (...) {
+        cur_frame_ = nullptr;
+        throw;
+    }
     last_launches_ = car_->last_launches();
     last_flops_ = car_->net().flops_per_image() * n;
     last_car_ms_ = car_->last_forward_ms();
     last_armor_ms_ = 0.f;
     // ROIs of every frame, in frame order; (frame, car) of each ROI
-    std::vector<Roi> rois;
-    std::vector<std::vector<int>> roi_of_car(n);
+    batch_rois_.clear();
+    batch_roi_of_car_.assign(n, {});
     for (int f = 0; f < n; ++f) {
-        if (static_cast<int>(cars[f].size()) > max_cars_) cars[f].resize(max_cars_);
-        roi_of_car[f].assign(cars[f].size(), -1);
-        for (size_t i = 0; i < cars[f].size(); ++i) {
-            const Detection& c = cars[f][i];
+        std::vector<Detection>& cars = batch_cars_[f];
+        if (static_cast<int>(cars.size()) > max_cars_) cars.resize(max_cars_);
+        batch_roi_of_car_[f].assign(cars.size(), -1);
+        for (size_t i = 0; i < cars.size(); ++i) {
+            const Detection& c = cars[i];
             Roi r{static_cast<int>(c.x), static_cast<int>(c.y) + f * h, static_cast<int>(c.width), static_cast<int>(c.height)};
             if (r.w <= 0 || r.h <= 0) continue;
-            roi_of_car[f][i] = static_cast<int>(rois.size());
-            rois.push_back(r);
+            batch_roi_of_car_[f][i] = static_cast<int>(batch_rois_.size());
+            batch_rois_.push_back(r);
         }
     }
+    // the first armor chunk goes out now, so the host work that follows (the searches) overlaps it
+    if (!batch_rois_.empty()) {
+        const int m = static_cast<int>(std::min<size_t>(armor_->max_batch(), batch_rois_.size()));
+        armor_->enqueue(cur_frame_, cur_stride_, batch_rois_.data(), m);
+    }
+    mid_done_ = true;
+    return batch_cars_;
+}
+
+std::vector<std::vector<RobotRecord>> RobotDetector::finish_batch() {
+    batch_cars();
+    const uint8_t* dev = cur_frame_;
+    const int n = cur_n_, stride = cur_stride_;
+    cur_frame_ = nullptr;
+    mid_done_ = false;
+    const std::vector<std::vector<Detection>>& cars = batch_cars_;
+    const std::vector<Roi>& rois = batch_rois_;
+    const std::vector<std::vector<int>>& roi_of_car = batch_roi_of_car_;
     std::vector<std::vector<Detection>> armor_all(rois.size());
     const int chunk = armor_->max_batch();
     for (size_t r0 = 0; r0 < rois.size(); r0 += chunk) {
         const int m = static_cast<int>(std::min<size_t>(chunk, rois.size() - r0));
-        auto part = armor_->detect_device_rois(dev, stride, rois.data() + r0, m);
+        auto part = r0 == 0 ? armor_->collect() : armor_->detect_device_rois(dev, stride, rois.data() + r0, m);
         for (int i = 0; i < m; ++i) armor_all[r0 + i] = std::move(part[i]);
         last_launches_ += armor_->last_launches();
         last_armor_ms_ += armor_->last_forward_ms();

@@ -62,6 +62,7 @@ private:
     size_t pinned_frame_bytes_ = 0;
     uint8_t* staging_ = nullptr;            // the reference's dev_border_ptr_: [max_batch][H*W*3] u8
     LetterboxGeom *dev_geoms_ = nullptr, *pinned_geoms_ = nullptr;
+    std::vector<LetterboxGeom> uploaded_geoms_;   // what dev_geoms_ holds
     Detection* pinned_out_ = nullptr;
     int* pinned_counts_ = nullptr;
     int* pinned_cand_counts_ = nullptr;    // candidates per image before NMS (capacity check)
@@ -76,6 +77,7 @@ struct RobotRecord {
     int label = -1;
     float confidence = 0.f;
     std::vector<Detection> armors;
+    int car = -1;           // index of the car detection this robot was made from (rect == that car's box)
 };
 
 class RobotDetector {
@@ -92,9 +94,15 @@ public:
     int frames() const { return frames_; }
     std::vector<RobotRecord> detect_host(const uint8_t* bgr, int w, int h, int stride);
     std::vector<RobotRecord> detect_device(const uint8_t* dev_bgr, int w, int h, int stride);
-    // split form: begin() uploads / enqueues the car stage and returns at once, finish() does the rest
+    // split form: begin() uploads / enqueues the car stage and returns at once; cars() waits for the car stage,
+    // enqueues the armor stage and returns the car boxes (what Locator::search needs — it can run beside the armor
+    // network); finish() waits for the armor stage and assembles the robots (calls cars() itself if nobody did)
     void begin(const uint8_t* frame, bool on_device, int w, int h, int stride);
+    const std::vector<Detection>& cars();
     std::vector<RobotRecord> finish();
+    // same split for a batch: boxes of every frame's cars, in frame order
+    const std::vector<std::vector<Detection>>& batch_cars();
+    const std::vector<std::vector<Detection>>& last_batch_cars() const { return batch_cars_; }
     void set_stream(cudaStream_t s) { car_->set_stream(s); armor_->set_stream(s); }
     Detector& car() { return *car_; }
     Detector& armor() { return *armor_; }
@@ -117,6 +125,11 @@ private:
     const uint8_t* cur_frame_ = nullptr;
     int cur_w_ = 0, cur_h_ = 0, cur_stride_ = 0, cur_n_ = 0;
     int frames_ = 1;
+    bool mid_done_ = false;
+    std::vector<int> roi_of_car_;                       // single frame: armor batch slot of car i, -1 = no ROI
+    std::vector<std::vector<Detection>> batch_cars_;    // batch: cars per frame
+    std::vector<Roi> batch_rois_;
+    std::vector<std::vector<int>> batch_roi_of_car_;
     std::vector<RobotRecord> assemble(const std::vector<Detection>& cars, const std::vector<std::vector<Detection>>& armors);
 };
 

@@ -58,6 +58,7 @@ public:
     // the two halves of search(): everything enqueued / the one wait (several locators overlap their searches)
     void search_begin(const RectF* rects, int n, cudaStream_t s);
     void search_end(LocResult* results, int n, cudaStream_t s);
+    int max_robots() const { return max_robots_; }
     void search_device(const RectF* dev_rects, LocResult* dev_results, int n, cudaStream_t s);
 
     int wz() const { return calib_.wz; }

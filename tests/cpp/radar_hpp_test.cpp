@@ -73,6 +73,45 @@ int main(int argc, char** argv) {
                 run_once_same = r2[i].location()->x == robots[i].location()->x && r2[i].location()->z == robots[i].location()->z;
         }
     }
+    // throughput mode: two streams fed the same frame and cloud must both give the single-stream robots; then the
+    // exchange with a world of one returns this rank's record block
+    bool run_batch_same = true, exchange_ok = true;
+    {
+        radar::RobotDetector det2(argv[1], argv[2], radar::Size{W, H}, 12, 20, 4, 0.75f, 0.65f, 0.25f, 0.65f, 0.50f, 640, 640,
+                                  "images", 3, 5, true, 0, 2);
+        radar::Locator la(W, H, K, L2C, W2C), lb(W, H, K, L2C, W2C);
+        for (radar::Locator* l : {&la, &lb})
+            l->update(radar::CloudView{reinterpret_cast<const float*>(bg.data()), static_cast<int>(bg.size() / 12), 12});
+        std::vector<char> frames2(frame), clouds2(cloud);
+        frames2.insert(frames2.end(), frame.begin(), frame.end());
+        clouds2.insert(clouds2.end(), cloud.begin(), cloud.end());
+        const auto per_stream = radar::runBatch(
+            det2, {&la, &lb}, radar::ImageView{reinterpret_cast<const unsigned char*>(frames2.data()), W, H, W * 3},
+            radar::CloudView{reinterpret_cast<const float*>(clouds2.data()), static_cast<int>(cloud.size() / 12), 12});
+        run_batch_same = per_stream.size() == 2;
+        for (size_t f = 0; run_batch_same && f < 2; ++f) {
+            run_batch_same = per_stream[f].size() == robots.size();
+            for (size_t i = 0; run_batch_same && i < robots.size(); ++i) {
+                const radar::Robot& a = per_stream[f][i];
+                run_batch_same = a.label() == robots[i].label() && a.isLocated() == robots[i].isLocated() &&
+                                 a.rectf()->x == robots[i].rectf()->x && a.rectf()->height == robots[i].rectf()->height;
+                if (run_batch_same && robots[i].isLocated())
+                    run_batch_same = a.location()->x == robots[i].location()->x && a.location()->y == robots[i].location()->y;
+            }
+        }
+        radar::Exchange ex(radar::Exchange::uniqueId(), 0, 1, 0, 20);
+        ex.publish(robots);
+        const std::vector<float> all = ex.collect();
+        ex.close();
+        exchange_ok = all.size() == 20u * RMR_RECORD_FLOATS;
+        for (size_t i = 0; exchange_ok && i < 20; ++i) {
+            const float* r = all.data() + i * RMR_RECORD_FLOATS;
+            if (i >= robots.size()) { exchange_ok = r[0] == 0.f; continue; }
+            exchange_ok = r[0] == 1.f && r[1] == static_cast<float>(robots[i].label().value_or(-1)) &&
+                          (r[3] != 0.f) == robots[i].isLocated();
+            if (exchange_ok && robots[i].isLocated()) exchange_ok = r[4] == robots[i].location()->x && r[6] == robots[i].location()->z;
+        }
+    }
     // cv::imread stand-in: frame.jpg decoded on the device must be the bytes of frame.bgr (= cv2.imread of that file),
     // and detect(decoder, file) must give the robots of detect(frame)
     bool jpeg_same = false, jpeg_detect_same = false, jpeg_rejects = false;
@@ -92,7 +131,8 @@ int main(int argc, char** argv) {
             jpeg_rejects = true;
         }
     }
-    std::printf("{\"ctor_throws\": %s, \"run_once_same\": %s, \"jpeg_same\": %s, \"jpeg_detect_same\": %s, \"jpeg_rejects\": %s, \"robots\": [",
+    std::printf("{\"run_batch_same\": %s, \"exchange_ok\": %s, ", run_batch_same ? "true" : "false", exchange_ok ? "true" : "false");
+    std::printf("\"ctor_throws\": %s, \"run_once_same\": %s, \"jpeg_same\": %s, \"jpeg_detect_same\": %s, \"jpeg_rejects\": %s, \"robots\": [",
                 threw ? "true" : "false", run_once_same ? "true" : "false", jpeg_same ? "true" : "false",
                 jpeg_detect_same ? "true" : "false", jpeg_rejects ? "true" : "false");
     for (size_t i = 0; i < robots.size(); ++i) {

@@ -27,9 +27,14 @@ def test_cpp_host_run_once(tmp_path):
                           os.path.join(fx.GOLDEN, "frames", "0.jpg")],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
-    doc = json.loads(out.stdout)
+    # the document is the last line (a library banner, e.g. NCCL's version line, may precede it on stdout)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines, (out.stdout[-2000:], out.stderr[-2000:])
+    doc = json.loads(lines[-1])
     assert doc["ctor_throws"] is True
     assert doc["run_once_same"] is True      # radar::runOnce == update + cluster + detect + search
+    assert doc["run_batch_same"] is True     # radar::runBatch over two streams == the single-stream robots, twice
+    assert doc["exchange_ok"] is True        # radar::Exchange (NCCL all-gather, world of one) returns the record block
     assert doc["jpeg_same"] is True          # radar::JpegDecoder::imdecode == cv2.imread, byte for byte
     assert doc["jpeg_detect_same"] is True and doc["jpeg_rejects"] is True
     robots = doc["robots"]

@@ -47,10 +47,19 @@ class CudnnNet:
         self.out = self.g.outputs[0].name
         self.static = None
         self.dynamic = None
+        self._int_cache = {}
 
-    @staticmethod
-    def _ints(t):
-        return [int(v) for v in (t.tolist() if isinstance(t, torch.Tensor) else t)]
+    def _ints(self, t):
+        """Shape operands as Python ints.  They are constants (folded on the first call); a constant that also feeds
+        device arithmetic lives on the device, so its values are read back once and remembered — nothing is copied
+        on later calls, CUDA-graph capture included.  The tensor is kept with its values so its id stays unique."""
+        if not isinstance(t, torch.Tensor):
+            return [int(v) for v in t]
+        hit = self._int_cache.get(id(t))
+        if hit is None:
+            hit = (t, [int(v) for v in t.tolist()])
+            self._int_cache[id(t)] = hit
+        return hit[1]
 
     @torch.no_grad()
     def __call__(self, x):
