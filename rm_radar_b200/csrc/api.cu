@@ -631,7 +631,7 @@ int rmr_run_once(rmr_robot_detector_t* d, rmr_locator_t* l, const void* frame, i
         if (!d || !l || !out || !count) throw std::invalid_argument("null argument");
         if (xyz && (point_stride_bytes % 4 != 0 || point_stride_bytes < 12)) throw std::invalid_argument("bad point stride");
         // RMR_TRACE=1: host wall-clock of the stages of this call on stderr (us since entry), for tuning only
-        static const bool trace = [] { const char* e = std::getenv("RMR_TRACE"); return e && e[0] == '1'; }();
+        static const bool trace = [] { const char* e = std::getenv("RMR_TRACE"); return e && (e[0] == '1' || e[0] == '2'); }();
         const auto t0 = std::chrono::steady_clock::now();
         double t_us[5] = {0, 0, 0, 0, 0};
         auto stamp = [&](int i) { if (trace) t_us[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };

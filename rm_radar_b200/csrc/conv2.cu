@@ -178,10 +178,11 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         __syncwarp();
         tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
         tmem_relinquish();
-    } else if (warp >= 4) {
-        const int i = threadIdx.x - 128;
-        if (i < p.block_n) s_bias[i] = __ldg(p.bias + ch0 + i);
     }
+    // bias: a constant, fetched now but parked in a register — the CTA-wide barrier below must not wait for a global
+    // load (~700 cycles of the ~1600-cycle setup); the epilogue warps publish it among themselves later
+    float bias_reg = 0.f;
+    if (warp >= 4 && static_cast<int>(threadIdx.x) - 128 < p.block_n) bias_reg = __ldg(p.bias + ch0 + threadIdx.x - 128);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -505,7 +506,10 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 }
                 ow0 = nw0; oh0 = nh0; n0 = nn0;
             }
-            if (leader) bulk_wait_all();   // the global writes are complete before the CTA retires
+            // the staging tiles have been read out (each store was followed by wait_group.read); the writes themselves
+            // complete under the grid's own completion (what griddepcontrol.wait / the stream order of the next layer
+            // waits for).  RMR_EXIT_WAIT_ALL=1 waits for them here instead.
+            if (leader && p.exit_wait_all) bulk_wait_all();
             __syncwarp();
         }
     } else if (warp >= 4) {
@@ -519,6 +523,8 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         const int nvalid = min(p.block_n, p.cout - ch0);
         const bool vec = p.vec_ok != 0;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        if (static_cast<int>(threadIdx.x) - 128 < p.block_n) s_bias[threadIdx.x - 128] = bias_reg;
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
         if (!p.tma_epi) pdl_wait2();   // residual reads and output writes must follow the previous grid
         uint32_t it = 0;
         for (int mt = j0; mt < p.m_tiles; mt += p.gm, ++it) {
@@ -952,6 +958,8 @@ void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
     p.units_per_split = (units + p.splits - 1) / p.splits;
     p.ns_total = p.n_tiles * p.splits;
     p.gm = static_cast<int>(std::max<long>(1, std::min<long>(p.m_tiles, kSM / std::max(1, std::min(p.ns_total, kSM)))));
+    static const bool exit_wait_all = env_flag("RMR_EXIT_WAIT_ALL", false);
+    p.exit_wait_all = exit_wait_all ? 1 : 0;
     p.gm_w = p.gm % p.tiles_w;
     p.gm_h = (p.gm / p.tiles_w) % p.tiles_h;
     p.gm_n = p.gm / p.tiles_w / p.tiles_h;

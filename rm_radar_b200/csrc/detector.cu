@@ -1,5 +1,8 @@
 #include "detector.h"
 
+#include <chrono>
+#include <cstdio>
+
 #include "engine.h"
 
 #include <algorithm>
@@ -95,6 +98,11 @@ Detector::Detector(const std::string& engine_path, int classes, int image_w, int
     RMR_CUDA(cudaMallocHost(&pinned_out_, sizeof(Detection) * kMaxOut * max_batch));
     RMR_CUDA(cudaMallocHost(&pinned_counts_, sizeof(int) * max_batch));
     RMR_CUDA(cudaMallocHost(&pinned_cand_counts_, sizeof(int) * max_batch));
+    // the NMS kernel writes its results into the pinned buffers itself (device-visible under unified addressing)
+    RMR_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&post_.host_out), pinned_out_, 0));
+    RMR_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&post_.host_out_count), pinned_counts_, 0));
+    RMR_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&post_.host_cand_count), pinned_cand_counts_, 0));
+    post_.host_head = kHeadOut;
     RMR_CUDA(cudaEventCreate(&ev_fwd0_));
     RMR_CUDA(cudaEventCreate(&ev_fwd1_));
     frame_buffer(static_cast<size_t>(image_w) * image_h * 3);
@@ -127,8 +135,16 @@ uint8_t* Detector::frame_buffer(size_t bytes) {
 // enqueue(): everything up to the device->host copy of the survivors, asynchronously on stream_;
 // collect(): the one synchronisation + unpacking.  run() = enqueue + collect; the cascade uses the split
 // to overlap its own CPU work (and the Locator's launches) with the car network.
+namespace {
+const bool kTraceStages = [] { const char* e = std::getenv("RMR_TRACE"); return e && e[0] == '2'; }();
+}
+
 void Detector::enqueue(const uint8_t* dev_frame, int stride, const Roi* rois, int n) {
     pending_ = 0;
+    const auto h0 = std::chrono::steady_clock::now();
+    auto host_us = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h0).count(); };
+    if (kTraceStages && !ev_trace_[0])
+        for (auto& e : ev_trace_) RMR_CUDA(cudaEventCreate(&e));
     if (n == 0) return;   // Appendix B#8: the reference aborts inside TensorRT on an empty batch
     if (n > max_batch_) throw std::invalid_argument("batch larger than max_batch_size");
     RMR_CUDA(cudaSetDevice(device_));
@@ -151,17 +167,24 @@ void Detector::enqueue(const uint8_t* dev_frame, int stride, const Roi* rois, in
         RMR_CUDA(cudaMemcpyAsync(dev_geoms_, pinned_geoms_, sizeof(LetterboxGeom) * n, cudaMemcpyHostToDevice, stream_));
         uploaded_geoms_.assign(pinned_geoms_, pinned_geoms_ + n);
     }
+    if (kTraceStages) RMR_CUDA(cudaEventRecord(ev_trace_[0], stream_));
+    const double t_geom = host_us();
     launch_letterbox(dev_frame, stride, dev_geoms_, any_unclean, any_clean, n, staging_, net_->input(), input_w_,
                      input_h_, stream_);
     RMR_CUDA(cudaEventRecord(ev_fwd0_, stream_));
+    const double t_lb = host_us();
     net_->forward(n, stream_);
+    const double t_net = host_us();
     RMR_CUDA(cudaEventRecord(ev_fwd1_, stream_));
     launch_postprocess(net_->levels(), classes_, n, dev_geoms_, conf_thresh_, nms_thresh_, post_, stream_);
-    RMR_CUDA(cudaMemcpyAsync(pinned_counts_, post_.out_count, sizeof(int) * n, cudaMemcpyDeviceToHost, stream_));
-    RMR_CUDA(cudaMemcpyAsync(pinned_cand_counts_, post_.cand_count, sizeof(int) * n, cudaMemcpyDeviceToHost, stream_));
-    // survivors are few: copy a compact head of every image's list now, the rest only if an image has more
-    RMR_CUDA(cudaMemcpy2DAsync(pinned_out_, sizeof(Detection) * kMaxOut, post_.out, sizeof(Detection) * kMaxOut,
-                               sizeof(Detection) * kHeadOut, n, cudaMemcpyDeviceToHost, stream_));
+    if (kTraceStages) RMR_CUDA(cudaEventRecord(ev_trace_[1], stream_));
+    // counters and the first kHeadOut survivors of every image are already on their way: nms_restore_kernel writes them
+    // into the pinned buffers (PostBuffers::host_*); a longer list is copied in collect()
+    if (kTraceStages) {
+        RMR_CUDA(cudaEventRecord(ev_trace_[2], stream_));
+        std::fprintf(stderr, "  enqueue(n=%d) host us: geoms %.1f | letterbox launched %.1f | graph launched %.1f | all enqueued %.1f\n", n,
+                     t_geom, t_lb, t_net, host_us());
+    }
     int net_launches = 0;
     net_->plan_stats(n, &net_launches, nullptr, nullptr);
     last_launches_ = (any_clean ? 1 : 0) + (any_unclean ? letterbox_compat_launches() : 0) + net_launches + 2;
@@ -176,6 +199,14 @@ std::vector<std::vector<Detection>> Detector::collect() {
     RMR_CUDA(cudaSetDevice(device_));
     RMR_CUDA(cudaStreamSynchronize(stream_));
     RMR_CUDA(cudaEventElapsedTime(&last_forward_ms_, ev_fwd0_, ev_fwd1_));
+    if (kTraceStages) {
+        float lb = 0, post = 0, d2h = 0;
+        cudaEventElapsedTime(&lb, ev_trace_[0], ev_fwd0_);
+        cudaEventElapsedTime(&post, ev_fwd1_, ev_trace_[1]);
+        cudaEventElapsedTime(&d2h, ev_trace_[1], ev_trace_[2]);
+        std::fprintf(stderr, "  collect(n=%d) device us: letterbox %.1f | net %.1f | decode+nms %.1f | d2h %.1f\n", n, lb * 1e3,
+                     last_forward_ms_ * 1e3, post * 1e3, d2h * 1e3);
+    }
     int longest = 0;
     for (int i = 0; i < n; ++i) {
         // the reference returns every survivor; a truncated list would be a different result, so it is an error

@@ -68,6 +68,7 @@ private:
     int* pinned_cand_counts_ = nullptr;    // candidates per image before NMS (capacity check)
     int last_launches_ = 0;
     cudaEvent_t ev_fwd0_ = nullptr, ev_fwd1_ = nullptr;
+    cudaEvent_t ev_trace_[3] = {nullptr, nullptr, nullptr};   // RMR_TRACE=2: stage boundaries on the stream
     float last_forward_ms_ = 0.f;
 };
 

@@ -1,6 +1,7 @@
 #include "postprocess.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -21,8 +22,8 @@ struct LevelsArg {
 // threshold (NMSKernel's `row_conf < score_thresh`, detector.cu:339-343, hoisted in front so that
 // only survivors are decoded), then the exported Detect tail for that anchor (DFL softmax over 16
 // bins, dist2bbox, x stride — SURVEY.md Appendix A) and decodeKernel's cxcywh -> clamped xywh.
-__global__ void __launch_bounds__(256) decode_compact_kernel(LevelsArg la, int num_classes, float conf_thresh,
-                                                             float* __restrict__ cand, int* __restrict__ cand_count) {
+__device__ __forceinline__ void decode_anchor(const LevelsArg& la, int num_classes, float conf_thresh, float* __restrict__ cand,
+                                              int* __restrict__ cand_count) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int img = blockIdx.y;
     if (a >= la.anchors) return;
@@ -99,23 +100,24 @@ __device__ __forceinline__ float iou_xywh(const float4 a, const float4 b) {
 constexpr int kSmemCand = 1024;
 
 template <bool kShared>
-__device__ __forceinline__ void nms_restore_body(const float* __restrict__ c, int n, float4* sbox, float4* smeta,
+__device__ __forceinline__ void nms_restore_body(const float* c, int n, float4* sbox, float4* smeta,
                                                  int* sanchor, const LetterboxGeom& g, float nms_thresh,
                                                  Detection* __restrict__ out, int* __restrict__ out_count, int max_out,
-                                                 int* warp_tot, int* base) {
+                                                 int* warp_tot, int* base, Detection* __restrict__ host_out, int host_head,
+                                                 int* __restrict__ host_out_count) {
     if (kShared) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) sanchor[i] = __float_as_int(c[i * 8 + 6]);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sanchor[i] = __float_as_int(__ldcg(c + i * 8 + 6));
         __syncthreads();
     }
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float4 b0 = reinterpret_cast<const float4*>(c + i * 8)[0];
-        const float4 b1 = reinterpret_cast<const float4*>(c + i * 8)[1];
+        const float4 b0 = __ldcg(reinterpret_cast<const float4*>(c + i * 8));
+        const float4 b1 = __ldcg(reinterpret_cast<const float4*>(c + i * 8) + 1);
         const int anchor = __float_as_int(b1.z);
         int rank = 0;
         if (kShared) {
             for (int j = 0; j < n; ++j) rank += (sanchor[j] < anchor) ? 1 : 0;
         } else {
-            for (int j = 0; j < n; ++j) rank += (__float_as_int(c[j * 8 + 6]) < anchor) ? 1 : 0;
+            for (int j = 0; j < n; ++j) rank += (__float_as_int(__ldcg(c + j * 8 + 6)) < anchor) ? 1 : 0;
         }
         sbox[kShared ? rank : 2 * rank] = b0;
         smeta[kShared ? rank : 2 * rank] = b1;
@@ -157,6 +159,7 @@ __device__ __forceinline__ void nms_restore_body(const float* __restrict__ c, in
             d.label = label;
             d.confidence = conf;
             out[off] = d;
+            if (off < host_head) host_out[off] = d;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -166,32 +169,65 @@ __device__ __forceinline__ void nms_restore_body(const float* __restrict__ c, in
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out_count = *base;
+    if (threadIdx.x == 0) {
+        *out_count = *base;
+        if (host_out_count) *host_out_count = *base;
+    }
 }
 
-__global__ void __launch_bounds__(256) nms_restore_kernel(const float* __restrict__ cand,
-                                                          const int* __restrict__ cand_count, float* sorted_scratch,
-                                                          const LetterboxGeom* __restrict__ geoms, float nms_thresh,
-                                                          Detection* __restrict__ out, int* __restrict__ out_count,
-                                                          int max_out) {
-    const int img = blockIdx.x;
-    const int n = min(cand_count[img], kMaxCandidates);
-    const float* c = cand + static_cast<size_t>(img) * kMaxCandidates * 8;
-    __shared__ float4 s_box[kSmemCand];
-    __shared__ float4 s_meta[kSmemCand];
-    __shared__ int s_anchor[kSmemCand];
-    __shared__ int warp_tot[8];
-    __shared__ int base;
-    const LetterboxGeom g = geoms[img];
-    Detection* o = out + static_cast<size_t>(img) * max_out;
+struct NmsArgs {
+    const float* cand;
+    const int* cand_count;
+    float* sorted_scratch;
+    const LetterboxGeom* geoms;
+    float nms_thresh;
+    Detection* out;
+    int* out_count;
+    int max_out;
+    Detection* host_out;
+    int host_head;
+    int* host_out_count;
+    int* host_cand_count;
+};
+
+struct NmsShared {
+    float4 box[kSmemCand];
+    float4 meta[kSmemCand];
+    int anchor[kSmemCand];
+    int warp_tot[8];
+    int base;
+};
+
+__device__ __forceinline__ void nms_restore_image(const NmsArgs& a, int img, NmsShared& sh) {
+    const int n_raw = __ldcg(a.cand_count + img);
+    if (a.host_cand_count && threadIdx.x == 0) a.host_cand_count[img] = n_raw;
+    const int n = min(n_raw, kMaxCandidates);
+    const float* c = a.cand + static_cast<size_t>(img) * kMaxCandidates * 8;
+    const LetterboxGeom g = a.geoms[img];
+    Detection* o = a.out + static_cast<size_t>(img) * a.max_out;
+    Detection* ho = a.host_out ? a.host_out + static_cast<size_t>(img) * a.max_out : nullptr;
+    const int head = a.host_out ? a.host_head : 0;
+    int* hc = a.host_out_count ? a.host_out_count + img : nullptr;
     if (n <= kSmemCand) {
-        nms_restore_body<true>(c, n, s_box, s_meta, s_anchor, g, nms_thresh, o, out_count + img, max_out, warp_tot, &base);
+        nms_restore_body<true>(c, n, sh.box, sh.meta, sh.anchor, g, a.nms_thresh, o, a.out_count + img, a.max_out, sh.warp_tot,
+                               &sh.base, ho, head, hc);
     } else {
         // global scratch rows are [box float4][meta float4]: element i of either view sits at float4 index 2 i
-        float4* sorted = reinterpret_cast<float4*>(sorted_scratch + static_cast<size_t>(img) * kMaxCandidates * 8);
-        nms_restore_body<false>(c, n, sorted, sorted + 1, nullptr, g, nms_thresh, o, out_count + img, max_out, warp_tot,
-                                &base);
+        float4* sorted = reinterpret_cast<float4*>(a.sorted_scratch + static_cast<size_t>(img) * kMaxCandidates * 8);
+        nms_restore_body<false>(c, n, sorted, sorted + 1, nullptr, g, a.nms_thresh, o, a.out_count + img, a.max_out, sh.warp_tot,
+                                &sh.base, ho, head, hc);
     }
+}
+
+// the NMS stage alone (self-test hook)
+__global__ void __launch_bounds__(256) nms_restore_kernel(const NmsArgs a) {
+    __shared__ NmsShared sh;
+    nms_restore_image(a, blockIdx.x, sh);
+}
+
+__global__ void __launch_bounds__(256) decode_compact_kernel(LevelsArg la, int num_classes, float conf_thresh, float* cand,
+                                                             int* cand_count) {
+    decode_anchor(la, num_classes, conf_thresh, cand, cand_count);
 }
 
 }  // namespace
@@ -224,11 +260,13 @@ void launch_postprocess(const std::vector<HeadLevel>& levels, int num_classes, i
     }
     la.anchors = a0;
     RMR_CUDA(cudaMemsetAsync(pb.cand_count, 0, sizeof(int) * batch, s));
-    decode_compact_kernel<<<dim3((a0 + 255) / 256, batch), 256, 0, s>>>(la, num_classes, conf_thresh, pb.cand,
-                                                                         pb.cand_count);
     float* sorted = pb.cand + static_cast<size_t>(8) * kMaxCandidates * pb.max_batch;
-    nms_restore_kernel<<<batch, 256, 0, s>>>(pb.cand, pb.cand_count, sorted, dev_geoms, nms_thresh, pb.out,
-                                             pb.out_count, pb.max_out);
+    const NmsArgs na{pb.cand, pb.cand_count, sorted, dev_geoms, nms_thresh, pb.out, pb.out_count, pb.max_out,
+                     pb.host_out, pb.host_head, pb.host_out_count, pb.host_cand_count};
+    // (decode + NMS as one launch — the last decode block of an image running its NMS — measured no faster than two
+    // launches: 1.3033 vs 1.3025 ms per step)
+    decode_compact_kernel<<<dim3((a0 + 255) / 256, batch), 256, 0, s>>>(la, num_classes, conf_thresh, pb.cand, pb.cand_count);
+    nms_restore_kernel<<<batch, 256, 0, s>>>(na);
     RMR_CUDA(cudaGetLastError());
 }
 
@@ -255,7 +293,8 @@ std::vector<Detection> postprocess_selftest(const float* cand6, int n, float nms
         RMR_CUDA(cudaMemcpy(pb.cand, h.data(), sizeof(float) * 8 * n, cudaMemcpyHostToDevice));
         RMR_CUDA(cudaMemcpy(pb.cand_count, &n, sizeof(int), cudaMemcpyHostToDevice));
         float* sorted = pb.cand + static_cast<size_t>(8) * kMaxCandidates * pb.max_batch;
-        nms_restore_kernel<<<1, 256>>>(pb.cand, pb.cand_count, sorted, dg, nms_thresh, pb.out, pb.out_count, pb.max_out);
+        nms_restore_kernel<<<1, 256>>>(NmsArgs{pb.cand, pb.cand_count, sorted, dg, nms_thresh, pb.out, pb.out_count, pb.max_out,
+                                               nullptr, 0, nullptr, nullptr});
         RMR_CUDA(cudaGetLastError());
         int cnt = 0;
         RMR_CUDA(cudaMemcpy(&cnt, pb.out_count, sizeof(int), cudaMemcpyDeviceToHost));

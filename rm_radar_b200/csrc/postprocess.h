@@ -23,6 +23,13 @@ struct PostBuffers {
     int* out_count = nullptr;     // [batch] (survivors, may exceed max_out -> truncated on write)
     int max_out = 0;
     int max_batch = 0;
+    // optional host mirrors (pinned, device-visible): the NMS kernel writes the two counters and the first host_head
+    // detections of every image straight into them, so the step needs no device->host copy (three small copies cost
+    // 14-20 us per stage, profiles/r2_summary.md); longer lists are fetched from `out` on demand
+    Detection* host_out = nullptr;     // [batch][max_out], first host_head rows of each image are written
+    int* host_out_count = nullptr;     // [batch]
+    int* host_cand_count = nullptr;    // [batch]
+    int host_head = 0;
 };
 
 void post_alloc(PostBuffers& pb, int max_batch, int max_out);
