@@ -1,5 +1,6 @@
 #include "detector.h"
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 
@@ -103,6 +104,15 @@ Detector::Detector(const std::string& engine_path, int classes, int image_w, int
     RMR_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&post_.host_out_count), pinned_counts_, 0));
     RMR_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&post_.host_cand_count), pinned_cand_counts_, 0));
     post_.host_head = kHeadOut;
+    {
+        int* done = nullptr;
+        void* done_dev = nullptr;
+        RMR_CUDA(cudaMallocHost(&done, sizeof(int) * max_batch));
+        std::memset(done, 0, sizeof(int) * max_batch);
+        RMR_CUDA(cudaHostGetDevicePointer(&done_dev, done, 0));
+        pinned_done_ = done;
+        post_.host_done = static_cast<int*>(done_dev);
+    }
     RMR_CUDA(cudaEventCreate(&ev_fwd0_));
     RMR_CUDA(cudaEventCreate(&ev_fwd1_));
     frame_buffer(static_cast<size_t>(image_w) * image_h * 3);
@@ -116,7 +126,7 @@ Detector::~Detector() {
     if (ev_fwd0_) cudaEventDestroy(ev_fwd0_);
     if (ev_fwd1_) cudaEventDestroy(ev_fwd1_);
     cudaFree(staging_); cudaFree(dev_geoms_); cudaFree(dev_frame_);
-    cudaFreeHost(pinned_geoms_); cudaFreeHost(pinned_out_); cudaFreeHost(pinned_counts_); cudaFreeHost(pinned_cand_counts_); cudaFreeHost(pinned_frame_);
+    cudaFreeHost(pinned_geoms_); cudaFreeHost(pinned_out_); cudaFreeHost(pinned_counts_); cudaFreeHost(pinned_cand_counts_); cudaFreeHost(const_cast<int*>(pinned_done_)); cudaFreeHost(pinned_frame_);
     net_.reset();
     if (own_stream_) cudaStreamDestroy(own_stream_);
 }
@@ -176,6 +186,7 @@ void Detector::enqueue(const uint8_t* dev_frame, int stride, const Roi* rois, in
     net_->forward(n, stream_);
     const double t_net = host_us();
     RMR_CUDA(cudaEventRecord(ev_fwd1_, stream_));
+    post_.seq = ++seq_;   // what the NMS blocks of this call store into their completion flags
     launch_postprocess(net_->levels(), classes_, n, dev_geoms_, conf_thresh_, nms_thresh_, post_, stream_);
     if (kTraceStages) RMR_CUDA(cudaEventRecord(ev_trace_[1], stream_));
     // counters and the first kHeadOut survivors of every image are already on their way: nms_restore_kernel writes them
@@ -197,8 +208,28 @@ std::vector<std::vector<Detection>> Detector::collect() {
     std::vector<std::vector<Detection>> results(n);
     if (n == 0) return results;
     RMR_CUDA(cudaSetDevice(device_));
-    RMR_CUDA(cudaStreamSynchronize(stream_));
-    RMR_CUDA(cudaEventElapsedTime(&last_forward_ms_, ev_fwd0_, ev_fwd1_));
+    // The results are written into pinned memory by the NMS kernel itself, one completion flag per image last: watching
+    // the flags returns a few microseconds after the last write, a stream synchronise only after the kernel has retired
+    // and the driver has noticed.  Bounded: after ~2 ms of watching (or with RMR_SYNC_WAIT=1) fall back to the synchronise,
+    // which also surfaces any launch failure.
+    static const bool sync_wait = [] { const char* e = std::getenv("RMR_SYNC_WAIT"); return e && e[0] == '1'; }();
+    bool seen = false;
+    if (!sync_wait) {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (long spins = 0; !seen; ++spins) {
+            seen = true;
+            for (int i = 0; i < n; ++i) seen = seen && (pinned_done_[i] == seq_);
+            if (!seen && (spins & 1023) == 1023 &&
+                std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) break;
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    }
+    if (!seen) RMR_CUDA(cudaStreamSynchronize(stream_));
+    if (cudaEventElapsedTime(&last_forward_ms_, ev_fwd0_, ev_fwd1_) != cudaSuccess) {
+        (void)cudaGetLastError();   // cudaErrorNotReady is not an error of ours
+        RMR_CUDA(cudaStreamSynchronize(stream_));
+        RMR_CUDA(cudaEventElapsedTime(&last_forward_ms_, ev_fwd0_, ev_fwd1_));
+    }
     if (kTraceStages) {
         float lb = 0, post = 0, d2h = 0;
         cudaEventElapsedTime(&lb, ev_trace_[0], ev_fwd0_);

@@ -66,6 +66,8 @@ private:
     Detection* pinned_out_ = nullptr;
     int* pinned_counts_ = nullptr;
     int* pinned_cand_counts_ = nullptr;    // candidates per image before NMS (capacity check)
+    volatile int* pinned_done_ = nullptr;  // completion flag per image, written by the NMS kernel (PostBuffers::host_done)
+    int seq_ = 0;
     int last_launches_ = 0;
     cudaEvent_t ev_fwd0_ = nullptr, ev_fwd1_ = nullptr;
     cudaEvent_t ev_trace_[3] = {nullptr, nullptr, nullptr};   // RMR_TRACE=2: stage boundaries on the stream

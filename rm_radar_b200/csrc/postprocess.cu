@@ -188,6 +188,8 @@ struct NmsArgs {
     int host_head;
     int* host_out_count;
     int* host_cand_count;
+    int* host_done;
+    int seq;
 };
 
 struct NmsShared {
@@ -223,6 +225,12 @@ __device__ __forceinline__ void nms_restore_image(const NmsArgs& a, int img, Nms
 __global__ void __launch_bounds__(256) nms_restore_kernel(const NmsArgs a) {
     __shared__ NmsShared sh;
     nms_restore_image(a, blockIdx.x, sh);
+    if (a.host_done) {
+        // every thread's host-visible writes are ordered before the flag: fence, block barrier, one store
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(a.host_done + blockIdx.x) = a.seq;
+    }
 }
 
 __global__ void __launch_bounds__(256) decode_compact_kernel(LevelsArg la, int num_classes, float conf_thresh, float* cand,
@@ -262,7 +270,7 @@ void launch_postprocess(const std::vector<HeadLevel>& levels, int num_classes, i
     RMR_CUDA(cudaMemsetAsync(pb.cand_count, 0, sizeof(int) * batch, s));
     float* sorted = pb.cand + static_cast<size_t>(8) * kMaxCandidates * pb.max_batch;
     const NmsArgs na{pb.cand, pb.cand_count, sorted, dev_geoms, nms_thresh, pb.out, pb.out_count, pb.max_out,
-                     pb.host_out, pb.host_head, pb.host_out_count, pb.host_cand_count};
+                     pb.host_out, pb.host_head, pb.host_out_count, pb.host_cand_count, const_cast<int*>(pb.host_done), pb.seq};
     // (decode + NMS as one launch — the last decode block of an image running its NMS — measured no faster than two
     // launches: 1.3033 vs 1.3025 ms per step)
     decode_compact_kernel<<<dim3((a0 + 255) / 256, batch), 256, 0, s>>>(la, num_classes, conf_thresh, pb.cand, pb.cand_count);
@@ -294,7 +302,7 @@ std::vector<Detection> postprocess_selftest(const float* cand6, int n, float nms
         RMR_CUDA(cudaMemcpy(pb.cand_count, &n, sizeof(int), cudaMemcpyHostToDevice));
         float* sorted = pb.cand + static_cast<size_t>(8) * kMaxCandidates * pb.max_batch;
         nms_restore_kernel<<<1, 256>>>(NmsArgs{pb.cand, pb.cand_count, sorted, dg, nms_thresh, pb.out, pb.out_count, pb.max_out,
-                                               nullptr, 0, nullptr, nullptr});
+                                               nullptr, 0, nullptr, nullptr, nullptr, 0});
         RMR_CUDA(cudaGetLastError());
         int cnt = 0;
         RMR_CUDA(cudaMemcpy(&cnt, pb.out_count, sizeof(int), cudaMemcpyDeviceToHost));

@@ -30,6 +30,10 @@ struct PostBuffers {
     int* host_out_count = nullptr;     // [batch]
     int* host_cand_count = nullptr;    // [batch]
     int host_head = 0;
+    // completion flags: block `img` of the NMS kernel stores `seq` into host_done[img] after a system-wide fence, so the
+    // host can watch the pinned word instead of paying a stream-synchronise wake-up
+    volatile int* host_done = nullptr; // [batch]
+    int seq = 0;
 };
 
 void post_alloc(PostBuffers& pb, int max_batch, int max_out);
