@@ -455,7 +455,7 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": ncu_traffic()[0], "peak_source": peak_src,
-                     "kernel": "conv_umma_kernel (tcgen05 implicit GEMM), all conv launches of one frame",
+                     "kernel": "conv2_kernel (tcgen05 implicit GEMM, csrc/conv2.cu), all conv launches of one frame",
                      "flops_per_step": stats["conv_flops"], "conv_ms_per_step": conv_ms,
                      "conv_launches_per_step": conv_launches,
                      "flops_per_launch": stats["conv_flops"] / max(conv_launches, 1),
