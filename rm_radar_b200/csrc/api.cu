@@ -961,6 +961,9 @@ int rmr_postprocess_selftest(const float* candidates, int n, float nms_thresh, r
 
 int rmr_conv_plan(int n, int h_in, int w_in, int cin, int cout, int k, int stride, int* out) {
     return guarded([&] {
+        if (!out) throw std::invalid_argument("null argument");
+        if (n < 1 || h_in < 1 || w_in < 1 || cin < 1 || cout < 1 || (k != 1 && k != 3) || (stride != 1 && stride != 2))
+            throw std::invalid_argument("conv plan: batch / extents must be positive, k in {1, 3}, stride in {1, 2}");
         const int pad = k / 2;
         ConvDesc d;
         d.n = n; d.h_in = h_in; d.w_in = w_in; d.cin = cin; d.cin_pad = cin; d.cout = cout; d.cout_pad = (cout + 15) / 16 * 16;
