@@ -58,6 +58,8 @@ struct Conv2Params {
     int tw, th, tn, tiles_w, tiles_h, tiles_n, m_tiles;
     int block_n, n_tiles, splits, ns_total;   // ns_total = n_tiles * splits: (channel slice, K split) pairs
     int gm;                                   // CTAs per pair; a CTA takes pixel tiles j, j + gm, ...
+    int in_pitch;                             // channel pitch of the input buffer (stride-2 halo: column parity = a channel offset)
+    uint32_t cls_stride;                      // stride-2 halo: bytes between the four parity-class patches of a stage
     int exit_wait_all;                        // 1: the DMA warp waits for its bulk stores to complete before the CTA retires
     int gm_w, gm_h, gm_n;                     // gm as a step in (tile_w, tile_h, tile_n): the kernel walks tiles without dividing
     int units_per_split;                      // split granularity: (tap, chunk) pairs, or channel chunks in halo mode

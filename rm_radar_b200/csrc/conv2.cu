@@ -239,7 +239,17 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                         if (dbg && leader && c == 0 && ti < 7 && !p.dbg_mode) dbg[2 + 8 * ti] = clock64();
                         if (leader) {
                             mbar_expect_tx(afull0 + aoff, p.a_tx);
-                            tma_load_4d(adst, &tm_a, afull0 + aoff, cx, ow0 - 1, oh0 - 1, n0);
+                            if (p.halo == 2) {
+                                // class (row parity pr, column parity pc): odd rows / columns start one pair earlier
+#pragma unroll
+                                for (int cls = 0; cls < 4; ++cls) {
+                                    const int pr = cls >> 1, pc = cls & 1;
+                                    tma_load_5d(adst + cls * p.cls_stride, &tm_a, afull0 + aoff, cx + pc * p.in_pitch, ow0 - pc, pr,
+                                                oh0 - pr, n0);
+                                }
+                            } else {
+                                tma_load_4d(adst, &tm_a, afull0 + aoff, cx, ow0 - 1, oh0 - 1, n0);
+                            }
                         }
                         __syncwarp();
                         aoff += 8u; adst += a_stage;
@@ -342,7 +352,13 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         const uint32_t a_kb_step = p.a_kb >> 4, b_kb_step = p.b_kb >> 4;      // per k-block
         const uint32_t b_in_stage = p.b_in_stage >> 4;
         const uint32_t tap_step = static_cast<uint32_t>(p.kpt) * b_kb_step;   // resident slice: k-blocks in weight order
-        const uint32_t dx_step = p.row_bytes >> 4, dy_step = (static_cast<uint32_t>(p.pw) * p.row_bytes) >> 4;
+        // operand tile of tap (dy, dx) inside a patch stage = row term + column term (16-byte units).  Stride 1: one
+        // 18 x pw patch, the tap is a shifted window.  Stride 2: four parity-class patches of 17 x 9; the middle row /
+        // column reads the even class, the outer ones the odd class, the far one shifted by one
+        const uint32_t row16 = p.row_bytes >> 4, pitch16 = (static_cast<uint32_t>(p.pw) * p.row_bytes) >> 4, cls16 = p.cls_stride >> 4;
+        const bool s2 = p.halo == 2;
+        const uint32_t ty0 = s2 ? 2u * cls16 : 0u, ty1 = s2 ? 0u : pitch16, ty2 = s2 ? 2u * cls16 + pitch16 : 2u * pitch16;
+        const uint32_t tx0 = s2 ? cls16 : 0u, tx1 = s2 ? 0u : row16, tx2 = s2 ? cls16 + row16 : 2u * row16;
         // barrier addresses: base + 8 * slot (the generic -> shared conversion is not free: once per role)
         const uint32_t afull0 = smem_u32(&bar_afull[0]), aempty0 = smem_u32(&bar_aempty[0]);
         const uint32_t bfull0 = smem_u32(&bar_bfull[0]), bempty0 = smem_u32(&bar_bempty[0]);
@@ -379,16 +395,16 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     if (resident) {
                         // nine k-blocks of MMAs and nothing else; the weight tile of (tap, chunk c) is k-block tap * kpt + c
                         if (leader) {
-                            uint32_t row_lo = a_lo, w_lo = b_lo;
+                            uint32_t w_lo = b_lo;
 #pragma unroll
                             for (int dy = 0; dy < 3; ++dy) {
+                                const uint32_t row_lo = a_lo + (dy == 0 ? ty0 : dy == 1 ? ty1 : ty2);
 #pragma unroll
                                 for (int dx = 0; dx < 3; ++dx) {
-                                    mma_kblock(acc, row_lo + dx * dx_step, w_lo, accumulate);
+                                    mma_kblock(acc, row_lo + (dx == 0 ? tx0 : dx == 1 ? tx1 : tx2), w_lo, accumulate);
                                     accumulate = 1;
                                     w_lo += tap_step;
                                 }
-                                row_lo += dy_step;
                             }
                             umma_commit(aempty0 + aoff);   // patch consumed
                         }
@@ -396,14 +412,14 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                         accumulate = 1;
                         b_lo += b_kb_step;   // next chunk
                     } else {
-                        uint32_t row_lo = a_lo;
 #pragma unroll 1
                         for (int dy = 0; dy < 3; ++dy) {
+                            const uint32_t row_lo = a_lo + (dy == 0 ? ty0 : dy == 1 ? ty1 : ty2);
                             mbar_wait_spin(bfull0 + boff, bphase);   // the three taps of this kernel row
                             if (leader) {
 #pragma unroll
                                 for (int dx = 0; dx < 3; ++dx) {
-                                    mma_kblock(acc, row_lo + dx * dx_step, b_lo + dx * b_kb_step, accumulate);
+                                    mma_kblock(acc, row_lo + (dx == 0 ? tx0 : dx == 1 ? tx1 : tx2), b_lo + dx * b_kb_step, accumulate);
                                     accumulate = 1;
                                 }
                                 umma_commit(bempty0 + boff);
@@ -411,7 +427,6 @@ conv2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                             }
                             __syncwarp();
                             accumulate = 1;
-                            row_lo += dy_step;
                             b_lo += b_step;
                             boff += 8u;
                             if (boff == bend) { boff = 0; bphase ^= 1u; b_lo = b_lo0; }
@@ -867,10 +882,21 @@ void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
     const int halo_min = env_int("RMR_HALO_MIN", 40);
     const bool halo_ok = d.k == 3 && S == 1 && d.h_out >= halo_min && d.w_out >= halo_min &&
                          (p.bk == 64 || env_flag("RMR_HALO32", true));
-    p.halo = (env_flag("RMR_HALO", true) && halo_ok) ? 1 : 0;
-    if (p.halo) {
+    // stride 2: the nine taps of an 8 x 16 output tile read four parity classes of the input (even / odd rows x even /
+    // odd columns), each a dense 9 x 17 pixel patch in the (pixel pair, parity) view the per-tap mode already uses —
+    // four boxes per channel chunk instead of nine strided ones, half the rows (p.halo == 2)
+    // Only single-chunk layers (Cin <= 64) take it: there the accumulation order (tap by tap) is the per-tap mode's, so
+    // the results are bit-identical; with several chunks the order becomes chunk-major, which moved one near-tie of the
+    // armor NMS on asset frame 1 (two candidates 0.7010 / 0.7014) for a gain of < 1 % of the step.
+    const bool halo2_ok = d.k == 3 && S == 2 && p.kpt == 1 && d.h_out >= halo_min && d.w_out >= halo_min && d.w_in % 2 == 0 &&
+                          d.h_in % 2 == 0;
+    p.halo = (env_flag("RMR_HALO", true) && halo_ok) ? 1 : (env_flag("RMR_HALO_S2", true) && halo2_ok) ? 2 : 0;
+    if (p.halo == 1) {
         p.tw = 8; p.th = 16; p.tn = 1;
         p.pw = env_int("RMR_HALO_PW", 10);
+    } else if (p.halo == 2) {
+        p.tw = 8; p.th = 16; p.tn = 1;
+        p.pw = 9;
     } else {
         long best = -1;
         for (int tw = 128; tw >= 1; tw >>= 1)
@@ -906,6 +932,17 @@ void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
         if (d.cout_pad % bn != 0) continue;
         if (force_n && bn != force_n && d.cout_pad % force_n == 0) continue;
         if (tma_epi_ok && bn % 32 != 0) continue;
+        bool single_patch_slot = false;
+        if (p.halo == 2) {
+            // one 4-class patch stage + two weight stages of three taps (or the resident slice) + the staging tile must
+            // fit; with room for one patch slot only, loading a patch and multiplying it take turns
+            const long a_stage2 = (4L * ((17L * 9L * p.row_bytes + 127L) & ~127L) + 1023L) & ~1023L;
+            const long b_stream = 2L * 3L * bn * p.bk * 2L, b_res = 9L * p.kpt * bn * p.bk * 2L;
+            const long stg = tma_epi_ok ? 128L * bn * esize : 0L;
+            const long room = kSmemMax - 1024 - stg - std::min(b_stream, b_res);
+            if (a_stage2 > room) continue;
+            single_patch_slot = 2 * a_stage2 > room;
+        }
         const int n_tiles = d.cout_pad / bn;
         // split-K (deterministic: fp32 partial tiles through L2, last-arriving split reduces) stays available for
         // experiments (RMR_CONV_SPLITS=n) but is not planned: a partial tile is 128 x N x 4 B written and read
@@ -930,7 +967,8 @@ void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
             //   tensor  N / 2 clk
             //   smem    (A 4096 B + B 32 N B read by the MMA + bytes TMA writes for the slice) / 128 B/clk
             //   ingest  L2 -> SM: 125 B/clk for a lone SM, ~75 B/clk per SM when all 148 stream
-            const double a_write = p.halo ? 4096.0 * (18.0 * p.pw) / (9.0 * 128.0) : 4096.0;
+            const double a_write = p.halo == 1 ? 4096.0 * (18.0 * p.pw) / (9.0 * 128.0)
+                                   : p.halo == 2 ? 4096.0 * (4.0 * 17.0 * 9.0) / (9.0 * 128.0) : 4096.0;
             const double staging = tma_epi_ok ? 128.0 * bn * esize : 0.0;
             const bool resident = static_cast<double>(kb) * bn * p.bk * 2 + (p.halo ? 2.0 : 3.0) * 16384 + staging <= kSmemMax - 1024 &&
                                   (p.halo || tiles_per_cta > 1);
@@ -944,7 +982,7 @@ void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
             // (direct stores: one L1 request per thread and 16 bytes, 16 N cycles for an fp16 tile)
             const double epi = (tma_epi_ok ? 500.0 + bn * 4.0 : 400.0 + bn * 8.0 * esize * (d.res ? 2.0 : 1.0)) +
                                (splits > 1 ? 4000.0 + bn * 30.0 * splits : 0.0);
-            const double tile_cyc = std::max(kb * per_kb, epi);
+            const double tile_cyc = std::max(kb * per_kb + (single_patch_slot ? ups * 1600.0 : 0.0), epi);
             // per-CTA fixed cost: launch ramp, barrier init, TMEM allocation, first operands in flight, last epilogue
             const double cost = waves * (2400.0 + tiles_per_cta * tile_cyc + epi);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_n = bn; best_splits = splits; }
@@ -966,9 +1004,18 @@ void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
 
     // ---- shared-memory layout: [A (or joint) ring][weights: resident slice | halo stream ring][epilogue staging] ----
     p.b_kb = static_cast<uint32_t>(p.block_n) * p.bk * 2u;
-    if (p.halo) {
+    if (p.halo == 1) {
         p.a_tx = 18u * p.pw * p.row_bytes;
         p.a_kb = (p.a_tx + 1023u) & ~1023u;
+    } else if (p.halo == 2) {
+        // one parity class: 17 rows of 9 pixels.  Class bases are 128-byte aligned only (RMR_HALO_S2_ALIGN=1024 pads them
+        // to the swizzle period): TMA and UMMA both derive the swizzle phase from the absolute shared-memory address, and
+        // the 3.5 KB of padding per stage is what decides between one and two stages for the N = 64 layers
+        const uint32_t cls_tx = 17u * 9u * p.row_bytes;
+        const uint32_t al = static_cast<uint32_t>(env_int("RMR_HALO_S2_ALIGN", 128));
+        p.cls_stride = (cls_tx + al - 1u) / al * al;
+        p.a_tx = 4u * cls_tx;
+        p.a_kb = (4u * p.cls_stride + 1023u) & ~1023u;
     } else {
         p.a_tx = 128u * p.row_bytes;
         p.a_kb = p.a_tx;
@@ -1040,6 +1087,7 @@ void plan_conv2(const ConvDesc& d, ConvLaunch& l) {
             else t = make_int4((s == 1 ? 0 : 1) * d.in_pitch, s == 0 ? -1 : 0, r == 1 ? 0 : 1, r == 0 ? -1 : 0);
             p.tap[r * d.k + s] = t;
         }
+    p.in_pitch = d.in_pitch;
     p.out = d.out; p.out_pitch = d.out_pitch; p.out_coff = d.out_coff; p.out_f32 = d.out_f32;
     p.bias = d.bias;
     p.act = d.act ? (env_flag("RMR_SILU_EXP", false) ? 2 : 1) : 0;
@@ -1063,7 +1111,7 @@ void make_conv2_launch(const ConvDesc& d, ConvLaunch& l) {
     const CUtensorMapSwizzle swz = (p.bk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
 
     const cuuint64_t cp = static_cast<cuuint64_t>(d.in_pitch);
-    if (p.halo) {
+    if (p.halo == 1) {
         cuuint64_t dims[4] = {cp, static_cast<cuuint64_t>(d.w_in), static_cast<cuuint64_t>(d.h_in), static_cast<cuuint64_t>(d.n)};
         cuuint64_t strides[3] = {cp * 2, d.w_in * cp * 2, static_cast<cuuint64_t>(d.h_in) * d.w_in * cp * 2};
         cuuint32_t box[4] = {static_cast<cuuint32_t>(p.bk), static_cast<cuuint32_t>(p.pw), 18u, 1u};
@@ -1072,8 +1120,10 @@ void make_conv2_launch(const ConvDesc& d, ConvLaunch& l) {
         cuuint64_t dims[5] = {S * cp, static_cast<cuuint64_t>(d.w_in / S), static_cast<cuuint64_t>(S),
                               static_cast<cuuint64_t>(d.h_in / S), static_cast<cuuint64_t>(d.n)};
         cuuint64_t strides[4] = {S * cp * 2, d.w_in * cp * 2, S * d.w_in * cp * 2, static_cast<cuuint64_t>(d.h_in) * d.w_in * cp * 2};
-        cuuint32_t box[5] = {static_cast<cuuint32_t>(p.bk), static_cast<cuuint32_t>(p.tw), 1u, static_cast<cuuint32_t>(p.th),
-                             static_cast<cuuint32_t>(p.tn)};
+        // (channels of S adjacent pixels, pixel pairs, row parity, row pairs, image): a per-tap box is one parity of
+        // tw x th pixel pairs; a stride-2 halo box is one parity class of 9 x 17
+        cuuint32_t box[5] = {static_cast<cuuint32_t>(p.bk), static_cast<cuuint32_t>(p.halo == 2 ? 9 : p.tw), 1u,
+                             static_cast<cuuint32_t>(p.halo == 2 ? 17 : p.th), static_cast<cuuint32_t>(p.tn)};
         encode2(&l.tm_a, const_cast<__half*>(d.in), 5, dims, strides, box, swz);
     }
     {

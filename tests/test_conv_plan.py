@@ -48,7 +48,7 @@ def test_every_layer_gets_a_plan_that_fits(batch):
         assert 1 <= ctas <= SM, where
         assert sa >= 1 and sb >= 0, where
         if halo:
-            assert k == 3 and s == 1, where                       # halo patches serve 3x3 stride-1 only
+            assert k == 3 and s == halo, where                    # 1: one 18 x pw patch (stride 1); 2: four parity-class patches (stride 2)
         ho, wo = (h + 2 * (k // 2) - k) // s + 1, (w + 2 * (k // 2) - k) // s + 1
         want_mtiles = -(-wo // tw) * -(-ho // th) * -(-batch // tn)
         assert mtiles == want_mtiles, where

@@ -12,6 +12,8 @@ SHAPES = [
     (1, 160, 160, 32, 32, 3, 1, 1, 1, 0),     # C2f(64) bottleneck, BK=32 / SWIZZLE_64B, shortcut
     (1, 320, 320, 32, 64, 3, 2, 1, 0, 0),     # backbone layer 1, stride 2
     (1, 160, 160, 64, 128, 3, 2, 1, 0, 0),    # layer 3 stride 2
+    (3, 160, 160, 64, 128, 3, 2, 1, 0, 0),    # same, three images: the four parity-class patches must not bleed across images
+    (2, 80, 80, 128, 256, 3, 2, 1, 0, 0),     # stride 2 with two channel chunks per patch
     (1, 80, 80, 128, 128, 1, 1, 1, 0, 0),     # 1x1
     (1, 40, 40, 768, 256, 1, 1, 1, 0, 0),     # neck C2f cv1, K=768
     (1, 20, 20, 256, 256, 3, 1, 1, 1, 0),     # 20^2: ragged tiles (TW=4..)
