@@ -2,8 +2,10 @@
 
 The hot path shards by stream with no data-path collective; the only exchange is the fixed-size block
 of world-frame robot records every rank publishes once per step (the reference has no distributed
-code at all).  `torch.distributed` is the transport: NCCL over NVLink on the GPU box, gloo in the CPU
-tests.  Record layout (8 float32 per robot, `max_cars` rows per rank):
+code at all).  On the GPU box the exchange is the library's own (`rm_radar_b200.Comm` = `rmr_comm_*`, NCCL all-gather
+issued from `csrc/comm.cu`); this module is the host-side restatement of it over `torch.distributed` — the transport of
+the world-size-2 gloo tests on CPU, the checker of `rmr_comm_pack`, and the unpacking of a gathered block into robots.
+Record layout (8 float32 per robot, `max_cars` rows per rank):
     [valid, label (-1 = undetected), confidence, is_located, x, y, z (metres, world), rect area]
 """
 from __future__ import annotations
