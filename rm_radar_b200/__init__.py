@@ -639,12 +639,24 @@ class Comm:
     ID_BYTES, RECORD_FLOATS = 128, 8
 
     @staticmethod
+    def _nccl_first():
+        """The library resolves NCCL at run time (`dlopen libnccl.so.2`) and takes the instance the process already has.
+        torch bundles a newer NCCL under the same soname: if the system one were loaded first, a later `import torch`
+        in the same process would fail to resolve its symbols.  So, where torch is installed, it loads its NCCL first."""
+        try:
+            import torch  # noqa: F401
+        except ImportError:
+            pass
+
+    @staticmethod
     def unique_id() -> bytes:
+        Comm._nccl_first()
         buf = (C.c_uint8 * Comm.ID_BYTES)()
         _lib.check(_lib.load().rmr_comm_unique_id(buf))
         return bytes(buf)
 
     def __init__(self, unique_id: bytes, rank: int, world: int, device: int = 0, max_robots: int = 20):
+        Comm._nccl_first()
         self._lib = _lib.load()
         self._h = C.c_void_p()
         buf = (C.c_uint8 * Comm.ID_BYTES).from_buffer_copy(unique_id)

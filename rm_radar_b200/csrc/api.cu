@@ -637,8 +637,13 @@ int rmr_run_once(rmr_robot_detector_t* d, rmr_locator_t* l, const void* frame, i
         auto stamp = [&](int i) { if (trace) t_us[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
         // 1. car stage goes out first (upload + letterbox + network + decode/NMS + D2H), nothing waits
         d->impl->begin(static_cast<const uint8_t*>(frame), frame_on_device != 0, width, height, stride_bytes);
-        // 2. the locator's launches are issued while the car network runs (its own stream)
+        // 2. the locator's launches are issued while the car network runs (its own stream).  A host cloud queues behind a
+        //    host frame: the frame upload is the one copy on the critical path and should not share the link
+        //    (RMR_UPLOAD_CONCURRENT=1 lets the two copies overlap, for A/B timing)
         RMR_CUDA(cudaSetDevice(l->device));
+        static const bool upload_concurrent = [] { const char* e = std::getenv("RMR_UPLOAD_CONCURRENT"); return e && e[0] == '1'; }();
+        if (!frame_on_device && !cloud_on_device && xyz && !upload_concurrent)
+            RMR_CUDA(cudaStreamWaitEvent(l->stream, d->impl->frame_uploaded(), 0));
         if (cloud_on_device) l->impl->update_device(static_cast<const float*>(xyz), n_points, point_stride_bytes / 4, l->stream);
         else l->impl->update_host(static_cast<const float*>(xyz), n_points, point_stride_bytes / 4, l->stream);
         l->impl->cluster(l->stream);
@@ -707,6 +712,7 @@ int rmr_run_batch(rmr_robot_detector_t* d, rmr_locator_t* const* locators, int n
         for (int f = 0; f < n_frames; ++f) {
             rmr_locator_t* l = locators[f];
             RMR_CUDA(cudaSetDevice(l->device));
+            if (!frames_on_device && !clouds_on_device && xyz) RMR_CUDA(cudaStreamWaitEvent(l->stream, d->impl->frame_uploaded(), 0));
             const float* cloud = static_cast<const float*>(xyz) + f * cloud_floats;
             if (clouds_on_device) l->impl->update_device(cloud, n_points, point_stride_bytes / 4, l->stream);
             else l->impl->update_host(cloud, n_points, point_stride_bytes / 4, l->stream);

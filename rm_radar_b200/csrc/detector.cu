@@ -404,6 +404,11 @@ RobotDetector::RobotDetector(const std::string& car_engine, const std::string& a
     armor_ = std::make_unique<Detector>(armor_engine, armor_classes, image_w, image_h * frames, armor_batch, armor_nms, armor_conf,
                                         input_w, input_h, compat, device);
     armor_->set_stream(car_->stream());
+    RMR_CUDA(cudaEventCreateWithFlags(&ev_frame_, cudaEventDisableTiming));
+}
+
+RobotDetector::~RobotDetector() {
+    if (ev_frame_) cudaEventDestroy(ev_frame_);
 }
 
 // begin(): upload (host frames) and enqueue the car stage, nothing waits; finish(): the rest of
@@ -424,6 +429,7 @@ void RobotDetector::begin(const uint8_t* frame, bool on_device, int w, int h, in
         }
         dev = buf;
         dev_stride = w * 3;
+        RMR_CUDA(cudaEventRecord(ev_frame_, car_->stream()));
     }
     cur_frame_ = dev; cur_w_ = w; cur_h_ = h; cur_stride_ = dev_stride;
     mid_done_ = false;
@@ -530,6 +536,7 @@ void RobotDetector::begin_batch(const uint8_t* frames, bool on_device, int n, in
         const size_t bytes = static_cast<size_t>(stride) * h * n;
         uint8_t* buf = car_->frame_buffer(bytes);
         RMR_CUDA(cudaMemcpyAsync(buf, frames, bytes, cudaMemcpyHostToDevice, car_->stream()));
+        RMR_CUDA(cudaEventRecord(ev_frame_, car_->stream()));
         dev = buf;
     }
     cur_frame_ = dev; cur_w_ = w; cur_h_ = h; cur_stride_ = stride; cur_n_ = n;

@@ -90,11 +90,15 @@ public:
     RobotDetector(const std::string& car_engine, const std::string& armor_engine, int image_w, int image_h,
                   int armor_classes, int max_cars, float iou_thresh, float car_nms, float car_conf, float armor_nms,
                   float armor_conf, int input_w, int input_h, bool compat, int device, int frames = 1);
+    ~RobotDetector();
     // frames of one size, back to back in memory (frame i at frame + i * h * stride); begin_batch enqueues the car
     // stage for all of them and returns at once, finish_batch does the rest and returns the robots per frame
     void begin_batch(const uint8_t* frames, bool on_device, int n, int w, int h, int stride);
     std::vector<std::vector<RobotRecord>> finish_batch();
     int frames() const { return frames_; }
+    // recorded on the detector stream right after the host->device copy of the frame(s) of the current call: other
+    // uploads (the LiDAR cloud) queue behind it, so the frame — the one copy on the critical path — has the link to itself
+    cudaEvent_t frame_uploaded() const { return ev_frame_; }
     std::vector<RobotRecord> detect_host(const uint8_t* bgr, int w, int h, int stride);
     std::vector<RobotRecord> detect_device(const uint8_t* dev_bgr, int w, int h, int stride);
     // split form: begin() uploads / enqueues the car stage and returns at once; cars() waits for the car stage,
@@ -128,6 +132,7 @@ private:
     const uint8_t* cur_frame_ = nullptr;
     int cur_w_ = 0, cur_h_ = 0, cur_stride_ = 0, cur_n_ = 0;
     int frames_ = 1;
+    cudaEvent_t ev_frame_ = nullptr;
     bool mid_done_ = false;
     std::vector<int> roi_of_car_;                       // single frame: armor batch slot of car i, -1 = no ROI
     std::vector<std::vector<Detection>> batch_cars_;    // batch: cars per frame
